@@ -1,0 +1,149 @@
+"""`CudaRenderer`: the Python mirror of the Rust shim a maintainer would add to the reference
+(`RendererType::Cuda` + `impl Renderer for CudaRenderer`).
+
+Mirrors reference src/renderer/mod.rs:107-112 (`trait Renderer { fn render(&self, world, config) }`)
+and the PT branch of src/renderer/naive.rs:410-537 / tiled.rs:553-669: for every render setting whose
+integrator is PT it builds the integrator parameters exactly as
+`Integrator::from_settings_and_world` does (src/integrator/mod.rs:59-105), then calls
+`render_sampled`, which here is one call through the C ABI into the CUDA wavefront pipeline.
+There is no CPU fallback: if the CUDA library is missing, loading raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import curves as C
+from . import ffi
+from . import world as W
+from .loader import Config, RenderSettings
+
+F32 = np.float32
+
+
+@dataclass
+class PTSettings:
+    """PathTracingIntegrator fields (reference src/integrator/pt.rs:16-26)."""
+
+    width: int
+    height: int
+    min_samples: int
+    min_bounces: int
+    max_bounces: int
+    light_samples: int
+    only_direct: bool
+    wavelength_bounds: Tuple[float, float]
+    camera: int
+
+    @staticmethod
+    def from_render_settings(rs: RenderSettings, camera_index: int) -> "PTSettings":
+        if rs.integrator_type != "PT":
+            raise ValueError("CudaRenderer supports IntegratorKind::PT only (supported_integrators)")
+        if rs.medium_aware:
+            raise ValueError("medium_aware = true is out of scope (SURVEY.md §8f N1)")
+        if rs.max_bounces is None:
+            raise ValueError("max_bounces is required (src/integrator/mod.rs:70 unwrap)")
+        return PTSettings(
+            width=rs.width, height=rs.height, min_samples=rs.min_samples,
+            min_bounces=rs.min_bounces if rs.min_bounces is not None else 4,
+            max_bounces=rs.max_bounces, light_samples=rs.light_samples,
+            only_direct=bool(rs.only_direct) if rs.only_direct is not None else False,
+            wavelength_bounds=rs.wavelength_bounds or C.BOUNDED_VISIBLE_RANGE,
+            camera=camera_index,
+        )
+
+    def to_dict(self) -> dict:
+        d = dict(self.__dict__)
+        d["wavelength_bounds"] = list(self.wavelength_bounds)
+        return d
+
+    @staticmethod
+    def from_dict(d: dict) -> "PTSettings":
+        d = dict(d)
+        d["wavelength_bounds"] = tuple(d["wavelength_bounds"])
+        return PTSettings(**d)
+
+    def params(self, seed: int = 0, spp: Optional[int] = None, spp_offset: int = 0, spp_total: Optional[int] = None) -> ffi.RptRenderParams:
+        p = ffi.RptRenderParams()
+        p.width, p.height = self.width, self.height
+        p.spp = self.min_samples if spp is None else spp
+        p.spp_offset = spp_offset
+        p.spp_total = self.min_samples if spp_total is None else spp_total
+        p.min_bounces, p.max_bounces = self.min_bounces, self.max_bounces
+        p.light_samples, p.only_direct = self.light_samples, int(self.only_direct)
+        p.lambda_lo, p.lambda_hi = self.wavelength_bounds
+        p.camera = self.camera
+        p.seed = seed
+        return p
+
+
+def split_spp(total: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """(count, offset) of the samples-per-pixel share of `rank` (remainder to low ranks)."""
+    base, rem = divmod(total, world_size)
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return count, offset
+
+
+class CudaRenderer:
+    """Drop-in for NaiveRenderer / TiledRenderer on the PT path."""
+
+    def __init__(self, device: int = 0, num_lambda: int = 1024, seed: int = 0):
+        self.device, self.num_lambda, self.seed = device, num_lambda, seed
+        self.lib = ffi.load_library()
+
+    def supported_integrators(self) -> List[str]:
+        return ["PT"]
+
+    def make_scene(self, world: W.World, wavelength_bounds: Tuple[float, float]) -> ffi.Scene:
+        flat = ffi.FlatScene(world, wavelength_bounds[0], wavelength_bounds[1], self.num_lambda)
+        return ffi.Scene(self.lib, flat, self.device)
+
+    def render_sampled(self, scene: ffi.Scene, st: PTSettings, spp: Optional[int] = None, spp_offset: int = 0,
+                       spp_total: Optional[int] = None):
+        """-> (film (H, W, 4) float32 mean XYZ, counters). One C-ABI call; host film out."""
+        return scene.render_pt(st.params(self.seed, spp, spp_offset, spp_total))
+
+    def render(self, world: W.World, config: Config) -> Dict[str, np.ndarray]:
+        """trait Renderer::render: one film per render setting, keyed by filename."""
+        films = {}
+        scenes: Dict[Tuple[float, float], ffi.Scene] = {}
+        for i, rs in enumerate(config.render_settings):
+            st = PTSettings.from_render_settings(rs, config.camera_names_to_index[rs.camera_id])
+            if st.wavelength_bounds not in scenes:
+                scenes[st.wavelength_bounds] = self.make_scene(world, st.wavelength_bounds)
+            film, _ = self.render_sampled(scenes[st.wavelength_bounds], st)
+            films[rs.filename or f"render_{i}"] = film
+        for s in scenes.values():
+            s.close()
+        return films
+
+    # ---- multi-GPU: spp split + one NCCL reduce of the XYZ film -----------------------
+    def render_sampled_distributed(self, scene: ffi.Scene, st: PTSettings, rank: int, world_size: int):
+        """Each rank renders its share of min_samples into a device-resident SUM film, then one
+        torch.distributed reduce(sum) to rank 0 over NCCL, normalised on the device.
+        Returns a torch.cuda tensor (H, W, 4) on every rank (only rank 0 holds the result)."""
+        import torch
+        import torch.distributed as dist
+
+        count, offset = split_spp(st.min_samples, world_size, rank)
+        ptr, counters = scene.render_pt_device(st.params(self.seed, count, offset, 0))
+        film = device_tensor(ptr, (st.height, st.width, 4), self.device)
+        if world_size > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            scene.film_scale(film.data_ptr(), st.height * st.width, 1.0 / st.min_samples)
+            torch.cuda.synchronize(self.device)
+        return film, counters
+
+
+def device_tensor(ptr: int, shape, device: int):
+    """Zero-copy torch view of a library-owned device buffer (CUDA array interface v3)."""
+    import torch
+
+    class _Arr:
+        __cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+
+    return torch.as_tensor(_Arr(), device=f"cuda:{device}")
