@@ -46,6 +46,7 @@ constexpr float NORMAL_OFFSET = 0.001f;          // src/lib.rs:48
 constexpr uint32_t NONE_U32 = 0xFFFFFFFFu;
 
 thread_local std::string g_error;
+bool g_debug = false;  // rpto_debug_color() turns on a per-sample trace (stdout)
 
 // ---- math::Vec3 / Point3 (f32x4 newtypes; w handled implicitly) ---------------------------------
 struct V3 {
@@ -1124,6 +1125,9 @@ inline void random_walk(const RptScene &S, Ray ray, float lambda, uint32_t bounc
       V3 wo;
       Bsdf fe = material_generate_and_evaluate(S, hit.material, lambda, hit.u, hit.v, s.x, s.y, wi, wo);
       float f = fe.f, pdf = fe.pdf;
+      if (g_debug)
+        std::printf("[walk b%u] p=(%.7g %.7g %.7g) n=(%.7g %.7g %.7g) mat=%u beta=%.7g f=%.7g pdf=%.7g wo=(%.7g %.7g %.7g) wi=(%.7g %.7g %.7g) s=(%.7g %.7g %.7g) inst=%u prim=%u t=%.7g\n",
+                    bounce, hit.p.x, hit.p.y, hit.p.z, hit.n.x, hit.n.y, hit.n.z, hit.material, beta, f, pdf, wo.x, wo.y, wo.z, wi.x, wi.y, wi.z, s.x, s.y, s.z, hit.instance, hit.prim, hit.t);
       float cos_o = std::fabs(wo.z);
       if (std::isnan(pdf)) break;
       float rr = bounce >= rr_start ? std::fmin(f / pdf, 1.0f) : 1.0f;  // f32::min: NaN -> 1.0
@@ -1173,12 +1177,15 @@ inline float estimate_direct_illumination(const RptScene &S, float lambda, const
   cnt.shadow_rays++;
   cnt.true_rays++;
   Hit sh;
+  if (g_debug)
+    std::printf("[nee] dir=(%.7g %.7g %.7g) light_pdf=%.7g bsdf f=%.7g pdf=%.7g weight=%.7g bsdf_wo.z=%.7g\n", light_dir.x, light_dir.y, light_dir.z, light_pdf, b.f, b.pdf, weight, bsdf_wo.z);
   if (world_hit(S, shadow, 0.0f, INF_F, sh)) {
     if (RPT_MAT_IS_LIGHT(sh.material)) {
       Frame lf = frame_from_normal(sh.n);
       V3 lwi = to_local(lf, -light_dir);
       float le = material_emission(S, sh.material, lambda, lwi);
       float cos_i = std::fabs(lwi.z), cos_o = std::fabs(bsdf_wo.z);
+      if (g_debug) std::printf("[shadow] hit inst=%u prim=%u t=%.7g le=%.7g lwi.z=%.7g -> %.7g\n", sh.instance, sh.prim, sh.t, le, lwi.z, b.f * throughput * cos_i * cos_o * le * weight / light_pdf);
       return b.f * throughput * cos_i * cos_o * le * weight / light_pdf;
     }
   }
@@ -1256,6 +1263,7 @@ inline float pt_color(const RptScene &S, const RptRenderParams &P, uint32_t px, 
       energy += weight * vx.throughput * emission;
     } else if (vx.type == VT_LIGHT_INSTANCE) {  // pt.rs:512-561
       float emission = material_emission(S, vx.material, lambda, vx.local_wi);
+      if (g_debug) std::printf("[emit v%zu] emission=%.7g\n", index, emission);
       if (emission > 0.0f) {
         if (P.light_samples == 0 || prev.type == VT_CAMERA) {
           energy += vx.throughput * emission;
@@ -1445,6 +1453,47 @@ int rpto_render_pt(RptScene *S, const RptRenderParams *P, float *film, RptCounte
     counters->true_rays = c_true;
   }
   return 0;
+}
+
+// Debug: the walk vertices of one (pixel, sample). 16 floats per vertex:
+// type, point xyz, normal xyz, throughput, pdf_forward, material, instance, u, v, 0,0,0. Returns the vertex count.
+int rpto_debug_path(RptScene *S, const RptRenderParams *P, uint32_t px, uint32_t py, uint32_t sample, float *out, uint32_t cap) {
+  SampleCtx ctx{P->seed, py * P->width + px, sample, P->light_samples};
+  RptRand4 s0 = rpt_philox(ctx.seed, ctx.pixel, ctx.sample, 0);
+  RptRand4 s1 = rpt_philox(ctx.seed, ctx.pixel, ctx.sample, 1);
+  float cu = ((float)px + s0.x) / (float)P->width, cv = ((float)py + s0.y) / (float)P->height;
+  float lambda = P->lambda_lo + s0.z * (P->lambda_hi - P->lambda_lo);
+  Ray r = camera_get_ray(S->cameras[P->camera], s1.x, s1.y, clampf(cu, 0.0f, 1.0f - EPS_F), clampf(cv, 0.0f, 1.0f - EPS_F));
+  std::vector<Vertex> path;
+  Vertex first{};
+  first.type = VT_CAMERA;
+  first.point = r.o;
+  first.normal = r.d;
+  first.throughput = 1.0f;
+  first.pdf_forward = 100.0f;
+  path.push_back(first);
+  Counters cnt;
+  random_walk(*S, r, lambda, P->only_direct ? 1u : P->max_bounces, 1.0f, ctx, path, P->min_bounces, cnt);
+  uint32_t n = 0;
+  for (auto &v : path) {
+    if (n >= cap) break;
+    float *o = out + 16 * n++;
+    o[0] = (float)v.type; o[1] = v.point.x; o[2] = v.point.y; o[3] = v.point.z;
+    o[4] = v.normal.x; o[5] = v.normal.y; o[6] = v.normal.z; o[7] = v.throughput; o[8] = v.pdf_forward;
+    o[9] = (float)RPT_MAT_INDEX(v.material); o[10] = (float)v.instance; o[11] = v.u; o[12] = v.v; o[13] = lambda; o[14] = o[15] = 0.0f;
+  }
+  return (int)n;
+}
+
+float rpto_debug_color(RptScene *S, const RptRenderParams *P, uint32_t px, uint32_t py, uint32_t sample) {
+  g_debug = true;
+  Counters cnt;
+  float l;
+  float e = pt_color(*S, *P, px, py, sample, l, cnt);
+  g_debug = false;
+  std::printf("[color] energy=%.7g lambda=%.7g\n", e, l);
+  std::fflush(stdout);
+  return e;
 }
 
 // Per-sample radiance dump for debugging / sample-level parity: energy[pix*spp + s], lambda likewise.

@@ -1,0 +1,979 @@
+// rpt_device.cuh — device-side scene layout and per-ray functions of the PT path (sm_100a).
+//
+// Every function cites the reference file:line (gillett-hernandez/rust-pathtracer) whose
+// behaviour it reproduces. This is the product path: it never touches oracle/.
+//
+// Numerics: fp32 throughout like the reference; IEEE div/sqrt (no --use_fast_math); the library is
+// compiled with -fmad=false because Rust never contracts a*b+c into an FMA: a fused cross product turns
+// the exact 0 of an axis-aligned normal into 1e-9, which flips the tangent frame's copysign branch and
+// sends the path elsewhere. The hit/miss DECISION arithmetic of the ray/primitive tests additionally
+// spells its roundings out with __f*_rn intrinsics (parity check (a) of BASELINE.json). Explicit fmaf()
+// is used only in the BVH slab test, which prunes but never decides.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rpt.h"
+#include "../../include/rpt_rng.h"
+
+#define RPT_PI 3.14159265358979323846f
+#define RPT_TAU 6.28318530717958647692f
+#define RPT_EPS 1.1920929e-7f
+#define RPT_NORMAL_OFFSET 0.001f /* reference src/lib.rs:48 */
+#define RPT_NONE 0xFFFFFFFFu
+#define RPT_INF __int_as_float(0x7f800000)
+
+// ---------------------------------------------------------------------------------------------
+// Device scene (SoA buffers in HBM; pointers passed by value inside DevScene as a kernel param)
+// ---------------------------------------------------------------------------------------------
+
+// BVH2 node, 64 B = 4 x float4 (one 128-bit load each). Both children's boxes live in the parent,
+// so one node fetch decides both descents. child >= 0: inner node index; child < 0: leaf, ~child =
+// shape index (instance id in the TLAS, mesh-local triangle id in a BLAS).
+struct __align__(16) DevNode {
+  float4 lmin_lmaxx;  // l.min.xyz, l.max.x
+  float4 lmaxyz_rminxy;  // l.max.y, l.max.z, r.min.x, r.min.y
+  float4 rminz_rmax;  // r.min.z, r.max.xyz
+  int4 children;      // left, right, unused, unused
+};
+
+enum : uint32_t {
+  DI_KIND_MASK = 0x3u,
+  DI_AXIS_SHIFT = 2,        // 2 bits
+  DI_TWO_SIDED = 1u << 4,
+  DI_HAS_TRANSFORM = 1u << 5,
+};
+
+// Instance record, 144 B. rev/fwd are the upper 3x4 of Transform3.reverse / .forward.
+struct __align__(16) DevInstance {
+  float4 rev[3];
+  float4 fwd[3];
+  float4 origin_size0;  // origin.xyz, size[0] (or radius)
+  float size1;
+  uint32_t flags;     // kind | axis << 2 | two_sided | has_transform
+  uint32_t material;  // packed MaterialId override or RPT_NONE
+  int32_t blas_root;  // child-ref of the mesh's BLAS root (absolute node index, or ~tri for 1-triangle meshes)
+  uint32_t tri_base;  // first triangle of the mesh in the global triangle arrays
+  uint32_t order;     // position in the reference's flat-BVH candidate order (tie-break only)
+  uint32_t has_normals;
+  uint32_t pad;
+};
+
+struct DevTexture {
+  const float *texels;
+  uint32_t channels, width, height;
+  int32_t curves[4];
+};
+
+struct DevScene {
+  // acceleration structure
+  const DevNode *nodes;  // TLAS nodes first, then every BLAS
+  int32_t tlas_root;     // child-ref
+  uint32_t num_instances;
+  const DevInstance *instances;
+  const float4 *tri_verts;    // 3 float4 per triangle: p0|material, p1|order, p2|unused  (w lanes as bits)
+  const float4 *tri_normals;  // 3 float4 per triangle (only for meshes with shading normals)
+  // lights / materials / spectra
+  uint32_t num_lights;
+  const uint32_t *lights;
+  const RptMaterial *materials;
+  const float *curve_lut;
+  const float *cie_lut;
+  uint32_t num_lambda;
+  float lut_lo, lut_hi;
+  const DevTexture *textures;
+  const uint32_t *stack_tex;
+  const RptTexStack *stacks;
+  // environment
+  uint32_t env_kind;
+  float env_strength;
+  int32_t env_curve;
+  float env_angular_diameter;
+  float3 env_sun_dir;
+  int32_t env_texstack;
+  float4 env_rot_fwd[3], env_rot_rev[3];
+  uint32_t imap_rows, imap_cols, imap_marginal_n;
+  const float *imap_row_pdf, *imap_row_cdf, *imap_m_pdf, *imap_m_cdf;
+  float imap_marginal_integral;
+  float p_env;         // effective env sampling probability (1 when there are no lights)
+  float world_radius;  // World.radius (world/mod.rs:69-72); informational
+};
+
+// ---------------------------------------------------------------------------------------------
+// float3 helpers (math::Vec3 / Point3)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 f3(float4 v) { return make_float3(v.x, v.y, v.z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross(float3 a, float3 b) {
+  return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// dot product with the reference's rounding: three products, two adds, nothing fused
+__device__ __forceinline__ float dot_rn(float3 a, float3 b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ float norm_squared(float3 a) { return dot(a, a); }
+__device__ __forceinline__ float3 normalized(float3 a) { return a / sqrtf(dot(a, a)); }  // Vec3::normalized = v / norm
+__device__ __forceinline__ float signumf(float x) { return (x != x) ? x : copysignf(1.0f, x); }  // f32::signum
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+__device__ __forceinline__ float3 xform_point(const float4 *m, float3 p) {
+  return f3(m[0].x * p.x + m[0].y * p.y + m[0].z * p.z + m[0].w, m[1].x * p.x + m[1].y * p.y + m[1].z * p.z + m[1].w,
+            m[2].x * p.x + m[2].y * p.y + m[2].z * p.z + m[2].w);
+}
+__device__ __forceinline__ float3 xform_vec(const float4 *m, float3 v) {
+  return f3(m[0].x * v.x + m[0].y * v.y + m[0].z * v.z, m[1].x * v.x + m[1].y * v.y + m[1].z * v.z,
+            m[2].x * v.x + m[2].y * v.y + m[2].z * v.z);
+}
+__device__ __forceinline__ float3 xform_vec_transposed(const float4 *m, float3 v) {  // (M^T) v, 3x3 part
+  return f3(m[0].x * v.x + m[1].x * v.y + m[2].x * v.z, m[0].y * v.x + m[1].y * v.y + m[2].y * v.z,
+            m[0].z * v.x + m[1].z * v.y + m[2].z * v.z);
+}
+
+// math::TangentFrame::from_normal (Duff et al. 2017)
+struct Frame {
+  float3 t, b, n;
+};
+__device__ __forceinline__ Frame frame_from_normal(float3 n) {
+  float sign = copysignf(1.0f, n.z);
+  float a = -1.0f / (sign + n.z);
+  float b = n.x * n.y * a;
+  Frame f;
+  f.t = f3(1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x);
+  f.b = f3(b, sign + n.y * n.y * a, -n.y);
+  f.n = n;
+  return f;
+}
+__device__ __forceinline__ float3 to_local(const Frame &f, float3 v) { return f3(dot(f.t, v), dot(f.b, v), dot(f.n, v)); }
+__device__ __forceinline__ float3 to_world(const Frame &f, float3 v) { return f.t * v.x + f.b * v.y + f.n * v.z; }
+
+// math sampling helpers
+__device__ __forceinline__ float3 random_cosine_direction(float sx, float sy) {
+  float s, c;
+  sincosf(RPT_TAU * sx, &s, &c);
+  float r = sqrtf(sy);
+  return f3(c * r, s * r, sqrtf(1.0f - sy));
+}
+__device__ __forceinline__ float3 random_on_unit_sphere(float sx, float sy) {
+  float s, c;
+  sincosf(sx * RPT_TAU, &s, &c);
+  float z = sy * 2.0f - 1.0f;
+  float r = sqrtf(1.0f - z * z);
+  return f3(r * c, r * s, z);
+}
+__device__ __forceinline__ float3 random_in_unit_disk(float sx, float sy) {
+  float s, c;
+  sincosf(sx * RPT_TAU, &s, &c);
+  float v = sqrtf(sy);
+  return f3(c * v, s * v, 0.0f);
+}
+__device__ __forceinline__ float3 uv_to_direction(float u, float v) {
+  float st, ct, sp, cp;
+  sincosf((u - 0.5f) * RPT_TAU, &st, &ct);
+  sincosf(v * RPT_PI, &sp, &cp);
+  return f3(sp * ct, sp * st, cp);
+}
+__device__ __forceinline__ void direction_to_uv(float3 d, float &u, float &v) {
+  float theta = atan2f(d.y, d.x);
+  float phi = acosf(d.z);
+  u = theta / 2.0f / RPT_PI + 0.5f;
+  v = phi / RPT_PI;
+}
+__device__ __forceinline__ float power_heuristic(float a, float b) { return (a * a) / (a * a + b * b); }
+__device__ __forceinline__ float power_heuristic_generic(float a, float b) { return a / (a + b); }  // src/lib.rs:114-119
+__device__ __forceinline__ bool choose(float x, float split, float &rescaled) {  // Sample1D::choose
+  if (x < split) {
+    rescaled = clampf(x / split, 0.0f, 1.0f - RPT_EPS);
+    return true;
+  }
+  rescaled = clampf((x - split) / (1.0f - split), 0.0f, 1.0f - RPT_EPS);
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spectral LUTs (include/rpt.h: uniform grid, linear interpolation)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lut_eval(const float *__restrict__ lut, uint32_t n, float lo, float hi, float lambda) {
+  float x = (lambda - lo) / (hi - lo) * (float)(n - 1);
+  x = clampf(x, 0.0f, (float)(n - 1));
+  uint32_t i = (uint32_t)x;
+  if (i > n - 2) i = n - 2;
+  float t = x - (float)i;
+  float a = __ldg(lut + i), b = __ldg(lut + i + 1);
+  return __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
+}
+__device__ __forceinline__ float curve_eval(const DevScene &S, int32_t c, float lambda) {
+  return lut_eval(S.curve_lut + (size_t)c * S.num_lambda, S.num_lambda, S.lut_lo, S.lut_hi, lambda);
+}
+// Texture{1,4}::eval_at + TexStack::eval_at (texture.rs:101-116,134-142,258-266; vec2d.rs:34-42)
+__device__ __forceinline__ float texstack_eval(const DevScene &S, int32_t stack, float lambda, float u, float v) {
+  float energy = 0.0f;
+  RptTexStack st = S.stacks[stack];
+  for (uint32_t k = 0; k < st.count; ++k) {
+    const DevTexture &T = S.textures[S.stack_tex[st.first + k]];
+    float uu = clampf(u, 0.0f, 1.0f - RPT_EPS), vv = clampf(v, 0.0f, 1.0f - RPT_EPS);
+    size_t x = (size_t)(uu * (float)T.width), y = (size_t)(vv * (float)T.height);
+    const float *tx = T.texels + (y * T.width + x) * T.channels;
+    if (T.channels == 1) {
+      energy += curve_eval(S, T.curves[0], lambda) * __ldg(tx);
+    } else {
+      float s = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s += curve_eval(S, T.curves[c], lambda) * __ldg(tx + c);
+      energy += s;
+    }
+  }
+  return energy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ray / primitive tests
+// ---------------------------------------------------------------------------------------------
+struct LocalHit {  // reference HitRecord fields an aggregate produces (hittable.rs:7-16)
+  float t;
+  float3 p, n;
+  float u, v;
+  uint32_t material;
+};
+
+__device__ __forceinline__ float3 shuffle_axis(float3 v, uint32_t axis) {  // rect.rs:6-12
+  return axis == RPT_AXIS_X ? f3(v.z, v.y, v.x) : (axis == RPT_AXIS_Y ? f3(v.x, v.z, v.y) : v);
+}
+__device__ __forceinline__ float3 axis_vec(uint32_t axis) {
+  return axis == RPT_AXIS_X ? f3(1, 0, 0) : (axis == RPT_AXIS_Y ? f3(0, 1, 0) : f3(0, 0, 1));
+}
+
+// AARect::hit (rect.rs:69-112). Returns t only (decision part); rect_finish fills the record.
+__device__ __forceinline__ bool rect_test(const DevInstance &I, float3 o, float3 d, float t0, float t1, float tmax, float &t_out) {
+  uint32_t axis = (I.flags >> DI_AXIS_SHIFT) & 3u;
+  float3 org = f3(I.origin_size0);
+  float3 tmp_o = shuffle_axis(o - org, axis);
+  float3 tmp_d = shuffle_axis(d, axis);
+  if (tmp_d.z == 0.0f) return false;
+  float t = (-tmp_o.z) / tmp_d.z;
+  if (t <= t0 || t > t1 || t >= tmax) return false;
+  float xh = __fadd_rn(tmp_o.x, __fmul_rn(t, tmp_d.x)), yh = __fadd_rn(tmp_o.y, __fmul_rn(t, tmp_d.y));
+  float hx = I.origin_size0.w / 2.0f, hy = I.size1 / 2.0f;
+  if (xh < -hx || xh > hx || yh < -hy || yh > hy) return false;
+  t_out = t;
+  return true;
+}
+__device__ __forceinline__ void rect_finish(const DevInstance &I, float3 o, float3 d, float t, LocalHit &h) {
+  uint32_t axis = (I.flags >> DI_AXIS_SHIFT) & 3u;
+  float3 org = f3(I.origin_size0);
+  float3 tmp_o = shuffle_axis(o - org, axis);
+  float3 tmp_d = shuffle_axis(d, axis);
+  float xh = __fadd_rn(tmp_o.x, __fmul_rn(t, tmp_d.x)), yh = __fadd_rn(tmp_o.y, __fmul_rn(t, tmp_d.y));
+  float hx = I.origin_size0.w / 2.0f, hy = I.size1 / 2.0f;
+  float3 n = axis_vec(axis);
+  if ((I.flags & DI_TWO_SIDED) && dot(d, n) > 0.0f) n = -n;
+  h.t = t;
+  h.p = o + d * t;
+  h.u = (xh + hx) / I.origin_size0.w;
+  h.v = (yh + hy) / I.size1;
+  h.n = n;  // unit axis; HitRecord::new's normalisation is the identity here
+  h.material = RPT_MAT_PACK(RPT_MAT_TAG_MATERIAL, 0);
+}
+// Sphere::hit (sphere.rs:34-87)
+__device__ __forceinline__ bool sphere_test(const DevInstance &I, float3 o, float3 d, float t0, float t1, float tmax, float &t_out) {
+  float radius = I.origin_size0.w;
+  float3 oc = o - f3(I.origin_size0);
+  // b*b - a*c cancels catastrophically near the silhouette: keep every rounding of the reference
+  float a = dot_rn(d, d), b = dot_rn(oc, d), c = __fsub_rn(dot_rn(oc, oc), __fmul_rn(radius, radius));
+  float disc = __fsub_rn(__fmul_rn(b, b), __fmul_rn(a, c));
+  if (!(disc > 0.0f)) return false;
+  float ds = sqrtf(disc);
+  float time = (-b - ds) / a;
+  if (time < t1 && time > t0 && time < tmax) {
+    t_out = time;
+    return true;
+  }
+  time = (-b + ds) / a;
+  if (time < t1 && time > t0 && time < tmax) {
+    t_out = time;
+    return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void sphere_finish(const DevInstance &I, float3 o, float3 d, float t, LocalHit &h) {
+  float3 p = o + d * t;
+  h.t = t;
+  h.p = p;
+  h.u = h.v = 0.0f;
+  h.n = normalized((p - f3(I.origin_size0)) / I.origin_size0.w);
+  h.material = RPT_MAT_PACK(RPT_MAT_TAG_MATERIAL, 0);
+}
+// Disk::hit (disk.rs:31-62)
+__device__ __forceinline__ bool disk_test(const DevInstance &I, float3 o, float3 d, float t0, float t1, float tmax, float &t_out) {
+  float radius = I.origin_size0.w;
+  float3 tmp_o = o - f3(I.origin_size0);
+  if (d.z == 0.0f) return false;
+  float t = (-tmp_o.z) / d.z;
+  if (t <= t0 || t > t1 || t >= tmax) return false;
+  float xh = __fadd_rn(tmp_o.x, __fmul_rn(t, d.x)), yh = __fadd_rn(tmp_o.y, __fmul_rn(t, d.y));
+  if (__fadd_rn(__fmul_rn(xh, xh), __fmul_rn(yh, yh)) > __fmul_rn(radius, radius)) return false;
+  t_out = t;
+  return true;
+}
+__device__ __forceinline__ void disk_finish(const DevInstance &I, float3 o, float3 d, float t, LocalHit &h) {
+  float3 n = f3(0, 0, 1);
+  if (dot(d, n) > 0.0f && (I.flags & DI_TWO_SIDED)) n = -n;
+  h.t = t;
+  h.p = o + d * t;
+  h.u = h.v = 0.0f;
+  h.n = n;
+  h.material = RPT_MAT_PACK(RPT_MAT_TAG_MATERIAL, 0);
+}
+
+__device__ __forceinline__ float3 tri_shuffle(float3 v, uint32_t kz) {  // mesh.rs:12-19
+  return kz == 0 ? f3(v.y, v.z, v.x) : (kz == 1 ? f3(v.z, v.x, v.y) : v);
+}
+// MeshTriangleRef::hit (mesh.rs:67-198): watertight test, f64 fallback on zero edge functions.
+// Outputs t and the three barycentrics exactly as the reference computes them.
+__device__ __forceinline__ bool tri_test(float3 p0, float3 p1, float3 p2, float3 o, float3 d, float t0, float t1, float &t_out,
+                                         float &b0, float &b1, float &b2) {
+  float3 p0t = p0 - o, p1t = p1 - o, p2t = p2 - o;
+  float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  float mx = fmaxf(fmaxf(ax, ay), az);
+  uint32_t kz = 0;
+  if (ay >= mx) kz = 1;
+  if (az >= mx) kz = 2;  // ties -> highest axis index (mesh.rs:80-85)
+  float3 dd = tri_shuffle(d, kz);
+  p0t = tri_shuffle(p0t, kz);
+  p1t = tri_shuffle(p1t, kz);
+  p2t = tri_shuffle(p2t, kz);
+  float sx = -dd.x / dd.z, sy = -dd.y / dd.z, sz = 1.0f / dd.z;
+  p0t.x = __fadd_rn(p0t.x, __fmul_rn(sx, p0t.z));
+  p1t.x = __fadd_rn(p1t.x, __fmul_rn(sx, p1t.z));
+  p2t.x = __fadd_rn(p2t.x, __fmul_rn(sx, p2t.z));
+  p0t.y = __fadd_rn(p0t.y, __fmul_rn(sy, p0t.z));
+  p1t.y = __fadd_rn(p1t.y, __fmul_rn(sy, p1t.z));
+  p2t.y = __fadd_rn(p2t.y, __fmul_rn(sy, p2t.z));
+  float e0 = __fsub_rn(__fmul_rn(p1t.x, p2t.y), __fmul_rn(p1t.y, p2t.x));
+  float e1 = __fsub_rn(__fmul_rn(p2t.x, p0t.y), __fmul_rn(p2t.y, p0t.x));
+  float e2 = __fsub_rn(__fmul_rn(p0t.x, p1t.y), __fmul_rn(p0t.y, p1t.x));
+  if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+    e0 = (float)__dsub_rn(__dmul_rn((double)p2t.y, (double)p1t.x), __dmul_rn((double)p2t.x, (double)p1t.y));
+    e1 = (float)__dsub_rn(__dmul_rn((double)p0t.y, (double)p2t.x), __dmul_rn((double)p0t.x, (double)p2t.y));
+    e2 = (float)__dsub_rn(__dmul_rn((double)p1t.y, (double)p0t.x), __dmul_rn((double)p1t.x, (double)p0t.y));
+  }
+  if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+  float det = __fadd_rn(__fadd_rn(e0, e1), e2);
+  if (det == 0.0f) return false;
+  float z0 = __fmul_rn(p0t.z, sz), z1 = __fmul_rn(p1t.z, sz), z2 = __fmul_rn(p2t.z, sz);
+  float t_scaled = __fadd_rn(__fadd_rn(__fmul_rn(e0, z0), __fmul_rn(e1, z1)), __fmul_rn(e2, z2));
+  float lo = __fmul_rn(t0, det), hi = __fmul_rn(t1, det);
+  if ((det < 0.0f && (t_scaled >= lo || t_scaled < hi)) || (det > 0.0f && (t_scaled <= lo || t_scaled > hi))) return false;
+  float inv_det = 1.0f / det;
+  b0 = __fmul_rn(e0, inv_det);
+  b1 = __fmul_rn(e1, inv_det);
+  b2 = __fmul_rn(e2, inv_det);
+  t_out = __fmul_rn(t_scaled, inv_det);
+  return true;
+}
+
+// Robust slab test against one child box; tnear returned for ordering. Conservative (never rejects a
+// box the exact test accepts): the far plane is widened by 2*gamma(3) as in PBRT's Bounds3::IntersectP, and
+// a NaN lane (0 * inf) drops that axis' constraint. This is the one place that uses explicit FMAs
+// (t = b * inv_d - o * inv_d): it only prunes, it never decides a hit, so its rounding is parity-irrelevant.
+__device__ __forceinline__ bool slab_test(float3 bmin, float3 bmax, float3 oinv, float3 inv_d, float tmax, float &tnear) {
+  float tx0 = fmaf(bmin.x, inv_d.x, -oinv.x), tx1 = fmaf(bmax.x, inv_d.x, -oinv.x);
+  float ty0 = fmaf(bmin.y, inv_d.y, -oinv.y), ty1 = fmaf(bmax.y, inv_d.y, -oinv.y);
+  float tz0 = fmaf(bmin.z, inv_d.z, -oinv.z), tz1 = fmaf(bmax.z, inv_d.z, -oinv.z);
+  float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+  float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
+  tf *= 1.0000004f;  // 1 + 2*gamma(3)
+  tnear = tn;
+  return tn <= tf;
+}
+
+// Closest-hit result of a BVH query.
+struct TraceHit {
+  float t;
+  uint32_t inst, prim;
+};
+
+// Tie-break keys reproduce the reference's candidate-loop semantics (accelerator/mod.rs:143-175,
+// mesh.rs:331-357): candidates are visited in flat-BVH order and replace the current best when
+// `t <= closest` (rect, disk, triangle) or `t < closest` (sphere). Among equal-t candidates the winner
+// is therefore the LAST non-strict one in order, else the FIRST strict one. key = larger wins.
+__device__ __forceinline__ uint64_t tie_key(bool strict, uint32_t inst_order, uint32_t tri_order) {
+  uint64_t k = strict ? (uint64_t)(0x7FFFFFFFu - inst_order) : (0x80000000ull | inst_order);
+  return (k << 32) | tri_order;
+}
+
+#define RPT_STACK_SIZE 64
+#define RPT_SENTINEL 0x7FFFFFFF
+
+// Two-level closest-hit traversal (replaces World::hit -> Accelerator::hit -> FlatBVH::traverse ->
+// Instance::hit -> Mesh::hit; world/mod.rs:166, accelerator/mod.rs:86-178, lbvh.rs:172-213,
+// instance.rs:75-133, mesh.rs:314-360). Unlike the reference (F8) it prunes by the closest hit so far;
+// results are identical because pruned boxes cannot contain a closer hit.
+// `stack` is this thread's slice of the CTA's shared-memory traversal stack, strided by `stride`.
+template <bool ANY_HIT>
+__device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d, float tmax, int *stack, int stride, TraceHit &out) {
+  float closest = tmax;
+  uint64_t best_key = 0;
+  bool found = false;
+  out.t = RPT_INF;
+  out.inst = RPT_NONE;
+  out.prim = RPT_NONE;
+
+  float3 ro = o, rd = d;
+  float3 inv = f3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+  float3 oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+  int sp = 0;
+  int cur = S.tlas_root;
+  uint32_t cur_inst = RPT_NONE;  // != NONE while inside a BLAS
+  uint32_t cur_inst_order = 0, cur_tri_base = 0;
+
+  while (true) {
+    if (cur >= 0 && cur != RPT_SENTINEL) {
+      const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
+      float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+      int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
+      float tl, tr;
+      bool hl = slab_test(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), oinv, inv, closest, tl);
+      bool hr = slab_test(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), oinv, inv, closest, tr);
+      if (hl && hr) {
+        bool left_first = tl <= tr;
+        int near_c = left_first ? ch.x : ch.y, far_c = left_first ? ch.y : ch.x;
+        stack[sp * stride] = far_c;
+        ++sp;
+        cur = near_c;
+        continue;
+      } else if (hl) {
+        cur = ch.x;
+        continue;
+      } else if (hr) {
+        cur = ch.y;
+        continue;
+      }
+    } else if (cur == RPT_SENTINEL) {
+      // leaving a BLAS: back to the world-space ray
+      ro = o;
+      rd = d;
+      inv = f3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+      oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+      cur_inst = RPT_NONE;
+    } else {
+      uint32_t idx = (uint32_t)(~cur);
+      if (cur_inst == RPT_NONE) {
+        // TLAS leaf: an instance
+        const DevInstance &I = S.instances[idx];
+        uint32_t flags = I.flags;
+        float3 lo = o, ld = d;
+        if (flags & DI_HAS_TRANSFORM) {  // instance.rs:89-95: direction is NOT renormalised, t is shared
+          lo = xform_point(I.rev, o);
+          ld = xform_vec(I.rev, d);
+        }
+        uint32_t kind = flags & DI_KIND_MASK;
+        if (kind == RPT_AGG_MESH) {
+          stack[sp * stride] = RPT_SENTINEL;
+          ++sp;
+          ro = lo;
+          rd = ld;
+          inv = f3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+          oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+          cur_inst = idx;
+          cur_inst_order = I.order;
+          cur_tri_base = I.tri_base;
+          cur = I.blas_root;
+          continue;
+        }
+        float t;
+        bool hit;
+        // closest-so-far is passed as t1 exactly as the reference's candidate loop does; a candidate
+        // that passes with t == closest is resolved by tie_key (a strict sphere never gets that far).
+        if (kind == RPT_AGG_RECT)
+          hit = rect_test(I, lo, ld, 0.0f, closest, tmax, t);
+        else if (kind == RPT_AGG_SPHERE)
+          hit = sphere_test(I, lo, ld, 0.0f, closest, tmax, t);
+        else
+          hit = disk_test(I, lo, ld, 0.0f, closest, tmax, t);
+        if (hit) {
+          uint64_t key = tie_key(kind == RPT_AGG_SPHERE, I.order, 0);
+          if (!found || t < closest || key > best_key) {
+            closest = t;
+            best_key = key;
+            found = true;
+            out.t = t;
+            out.inst = idx;
+            out.prim = 0;
+            if (ANY_HIT) return true;
+          }
+        }
+      } else {
+        // BLAS leaf: a triangle of the current mesh instance
+        uint32_t tri = cur_tri_base + idx;
+        const float4 *tv = S.tri_verts + 3 * (size_t)tri;
+        float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
+        float t, b0, b1, b2;
+        if (tri_test(f3(v0), f3(v1), f3(v2), ro, rd, 0.0f, closest, t, b0, b1, b2)) {
+          uint64_t key = tie_key(false, cur_inst_order, __float_as_uint(v1.w));
+          if (!found || t < closest || key > best_key) {
+            closest = t;
+            best_key = key;
+            found = true;
+            out.t = t;
+            out.inst = cur_inst;
+            out.prim = idx;
+            if (ANY_HIT) return true;
+          }
+        }
+      }
+    }
+    if (sp == 0) break;
+    --sp;
+    cur = stack[sp * stride];
+  }
+  return found;
+}
+
+// Full hit record of a known (instance, primitive, t): Instance::hit's output (instance.rs:96-116).
+struct SurfaceHit {
+  float3 p, n;
+  float u, v;
+  uint32_t material;
+};
+__device__ __forceinline__ void reconstruct_hit(const DevScene &S, float3 o, float3 d, const TraceHit &th, SurfaceHit &sh) {
+  const DevInstance &I = S.instances[th.inst];
+  uint32_t flags = I.flags;
+  float3 lo = o, ld = d;
+  if (flags & DI_HAS_TRANSFORM) {
+    lo = xform_point(I.rev, o);
+    ld = xform_vec(I.rev, d);
+  }
+  LocalHit h;
+  uint32_t kind = flags & DI_KIND_MASK;
+  if (kind == RPT_AGG_MESH) {
+    uint32_t tri = I.tri_base + th.prim;
+    const float4 *tv = S.tri_verts + 3 * (size_t)tri;
+    float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
+    float3 p0 = f3(v0), p1 = f3(v1), p2 = f3(v2);
+    float t, b0, b1, b2;
+    // same arithmetic as the trace kernel -> same t and barycentrics (deterministic); t1 = +inf
+    tri_test(p0, p1, p2, lo, ld, 0.0f, RPT_INF, t, b0, b1, b2);
+    float3 n;
+    if (I.has_normals) {
+      const float4 *tn = S.tri_normals + 3 * (size_t)tri;
+      n = b0 * f3(__ldg(tn)) + b1 * f3(__ldg(tn + 1)) + b2 * f3(__ldg(tn + 2));  // mesh.rs:169-179
+    } else {
+      n = normalized(cross(p0 - p2, p1 - p2));  // mesh.rs:164-166
+    }
+    h.t = th.t;
+    h.p = b0 * p0 + b1 * p1 + b2 * p2;
+    h.u = h.v = 0.0f;
+    h.n = normalized(n);  // HitRecord::new (hittable.rs:34)
+    h.material = __float_as_uint(v0.w);
+  } else if (kind == RPT_AGG_RECT) {
+    rect_finish(I, lo, ld, th.t, h);
+  } else if (kind == RPT_AGG_SPHERE) {
+    sphere_finish(I, lo, ld, th.t, h);
+  } else {
+    disk_finish(I, lo, ld, th.t, h);
+  }
+  if (flags & DI_HAS_TRANSFORM) {
+    h.n = normalized(xform_vec_transposed(I.rev, h.n));
+    h.p = xform_point(I.fwd, h.p);
+  }
+  sh.p = h.p;
+  sh.n = h.n;
+  sh.u = h.u;
+  sh.v = h.v;
+  sh.material = I.material != RPT_NONE ? I.material : h.material;
+}
+
+// ---------------------------------------------------------------------------------------------
+// light sampling (Hittable::sample / psa_pdf through Instance)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float finite_or_zero(float p) { return isfinite(p) ? p : 0.0f; }
+// Instance::sample (instance.rs:134-141) over AARect / Sphere / Disk (rect.rs:113-155, sphere.rs:88-131, disk.rs:63-91)
+__device__ __forceinline__ void instance_sample(const DevInstance &I, float sx, float sy, float3 from, float3 &dir, float &pdf) {
+  uint32_t flags = I.flags;
+  uint32_t kind = flags & DI_KIND_MASK;
+  float3 f = (flags & DI_HAS_TRANSFORM) ? xform_point(I.rev, from) : from;
+  float3 org = f3(I.origin_size0);
+  float3 direction;
+  float p;
+  if (kind == RPT_AGG_SPHERE) {
+    float radius = I.origin_size0.w;
+    float3 n = random_on_unit_sphere(sx, sy);
+    float3 point = org + radius * n;
+    float area_pdf = 1.0f / (radius * radius * 4.0f * RPT_PI);
+    direction = point - f;
+    float ndd = fabsf(dot(n, normalized(direction)));
+    p = area_pdf * norm_squared(direction) / ndd;
+  } else {
+    uint32_t axis = (flags >> DI_AXIS_SHIFT) & 3u;
+    float3 n = kind == RPT_AGG_RECT ? axis_vec(axis) : f3(0, 0, 1);
+    float x = sx;
+    if (flags & DI_TWO_SIDED) {
+      float resc;
+      bool first = choose(x, 0.5f, resc);
+      x = resc;
+      n = n * (first ? -1.0f : 1.0f);
+    }
+    float3 point;
+    float area;
+    if (kind == RPT_AGG_RECT) {
+      point = org + shuffle_axis(f3((x - 0.5f) * I.origin_size0.w, (sy - 0.5f) * I.size1, 0.0f), axis);
+      area = I.origin_size0.w * I.size1;
+    } else {
+      float radius = I.origin_size0.w;
+      point = org + radius * random_in_unit_disk(x, sy);
+      area = RPT_PI * radius * radius;
+    }
+    direction = point - f;
+    float cos_i = dot(n, normalized(direction));
+    p = (1.0f / area) * norm_squared(direction) / fabsf(cos_i);  // Area -> SolidAngle
+  }
+  dir = normalized(direction);
+  pdf = finite_or_zero(p);
+  if (flags & DI_HAS_TRANSFORM) dir = normalized(xform_vec(I.fwd, dir));
+}
+// Instance::psa_pdf (instance.rs:154-170; rect.rs:156-173, sphere.rs:132-152, disk.rs:92-104)
+__device__ __forceinline__ float instance_psa_pdf(const DevInstance &I, float cos_o, float cos_i, float3 from, float3 to) {
+  uint32_t flags = I.flags;
+  if (flags & DI_HAS_TRANSFORM) {  // to_world (reference quirk Q11)
+    from = xform_point(I.fwd, from);
+    to = xform_point(I.fwd, to);
+  }
+  float d2 = norm_squared(to - from);
+  uint32_t kind = flags & DI_KIND_MASK;
+  if (kind == RPT_AGG_RECT) {
+    float area_pdf = 1.0f / (I.origin_size0.w * I.size1);
+    return (area_pdf * d2 / fabsf(cos_i)) / fabsf(cos_o);
+  } else if (kind == RPT_AGG_SPHERE) {
+    float area_pdf = 1.0f / (I.origin_size0.w * I.origin_size0.w * 4.0f * RPT_PI);
+    return area_pdf * d2 / fabsf(cos_i * cos_o);
+  } else if (kind == RPT_AGG_DISK) {
+    float area = RPT_PI * I.origin_size0.w * I.origin_size0.w;
+    return d2 / ((fabsf(cos_o) * fabsf(cos_i) + 0.00001f) * area);
+  }
+  return 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// materials (materials/{lambertian,ggx,diffuse_light,sharp_light}.rs)
+// ---------------------------------------------------------------------------------------------
+struct Bsdf {
+  float f, pdf;
+};
+__device__ __forceinline__ float3 ggx_reflect(float3 wi, float3 n) {  // ggx.rs:3-6
+  float3 w = -wi;
+  return normalized(w - 2.0f * dot(w, n) * n);
+}
+__device__ __forceinline__ bool ggx_refract(float3 wi, float3 n, float eta, float3 &out) {  // ggx.rs:8-17
+  float cos_i = dot(wi, n);
+  float sin2i = fmaxf(1.0f - cos_i * cos_i, 0.0f);
+  float sin2t = eta * eta * sin2i;
+  if (sin2t >= 1.0f) return false;
+  float cos_t = sqrtf(1.0f - sin2t);
+  out = normalized(-wi * eta + n * (eta * cos_i - cos_t));
+  return true;
+}
+__device__ __forceinline__ float fresnel_dielectric(float eta_i, float eta_t, float cos_i) {  // ggx.rs:19-48
+  cos_i = clampf(cos_i, -1.0f, 1.0f);
+  if (cos_i < 0.0f) {
+    cos_i = -cos_i;
+    float tmp = eta_i;
+    eta_i = eta_t;
+    eta_t = tmp;
+  }
+  float sin_t = eta_i / eta_t * sqrtf(fmaxf(0.0f, 1.0f - cos_i * cos_i));
+  float cos_t = sqrtf(fmaxf(0.0f, 1.0f - sin_t * sin_t));
+  float ei_ct = eta_i * cos_t, et_ci = eta_t * cos_i, ei_ci = eta_i * cos_i, et_ct = eta_t * cos_t;
+  float r_par = (et_ci - ei_ct) / (et_ci + ei_ct);
+  float r_perp = (ei_ci - et_ct) / (ei_ci + et_ct);
+  return (r_par * r_par + r_perp * r_perp) / 2.0f;
+}
+__device__ __forceinline__ float fresnel_conductor(float eta_i, float eta_t, float k_t, float cos_theta_i) {  // ggx.rs:50-85
+  cos_theta_i = clampf(cos_theta_i, -1.0f, 1.0f);
+  if (cos_theta_i < 0.0f) {
+    cos_theta_i = -cos_theta_i;
+    float tmp = eta_i;
+    eta_i = eta_t;
+    eta_t = tmp;
+  }
+  float eta = eta_t / eta_i, etak = k_t / eta_i;
+  float c2 = cos_theta_i * cos_theta_i, s2 = 1.0f - c2;
+  float eta2 = eta * eta, etak2 = etak * etak;
+  float t0 = eta2 - etak2 - s2;
+  float a2plusb2 = sqrtf(t0 * t0 + eta2 * etak2 * 4.0f);
+  float t1 = a2plusb2 + c2;
+  float a = sqrtf((a2plusb2 + t0) * 0.5f);
+  float t2 = a * cos_theta_i * 2.0f;
+  float rs = (t1 - t2) / (t1 + t2);
+  float t3 = a2plusb2 * c2 + s2 * s2;
+  float t4 = t2 * s2;
+  float rp = rs * (t3 - t4) / (t3 + t4);
+  return (rs + rp) / 2.0f;
+}
+__device__ __forceinline__ float ggx_d(float alpha, float3 wm) {  // ggx.rs:87-97
+  float s0 = wm.x / alpha, s1 = wm.y / alpha;
+  float t = wm.z * wm.z + s0 * s0 + s1 * s1;
+  float a2 = alpha * alpha, t2 = t * t;
+  return 1.0f / (RPT_PI * (a2 * t2));
+}
+__device__ __forceinline__ float ggx_lambda(float alpha, float3 w) {  // ggx.rs:99-107
+  if (w.z == 0.0f) return 0.0f;
+  float a2 = alpha * alpha;
+  float c = 1.0f + (a2 * (w.x * w.x) + a2 * (w.y * w.y)) / (w.z * w.z);
+  return sqrtf(c) * 0.5f - 0.5f;
+}
+__device__ __forceinline__ float ggx_g(float alpha, float3 wi, float3 wo) { return 1.0f / (1.0f + ggx_lambda(alpha, wi) + ggx_lambda(alpha, wo)); }
+__device__ __forceinline__ float ggx_vnpdf(float alpha, float3 wi, float3 wh) {  // ggx.rs:115-119
+  float inv_gl = 1.0f + ggx_lambda(alpha, wi);
+  return (ggx_d(alpha, wh) * fabsf(dot(wi, wh))) / (inv_gl * fabsf(wi.z));
+}
+__device__ __forceinline__ float ggx_vnpdf_no_d(float alpha, float3 wi, float3 wh) {  // ggx.rs:121-123
+  return fabsf(dot(wi, wh) / ((1.0f + ggx_lambda(alpha, wi)) * wi.z));
+}
+__device__ __forceinline__ float3 ggx_sample_vndf(float alpha, float3 wi, float x, float y) {  // ggx.rs:129-169
+  float3 v = normalized(f3(alpha * wi.x, alpha * wi.y, wi.z));
+  float3 t1 = v.z < 0.9999f ? normalized(cross(v, f3(0, 0, 1))) : f3(1, 0, 0);
+  float3 t2 = cross(t1, v);
+  float a = 1.0f / (1.0f + v.z);
+  float r = sqrtf(x);
+  float phi = y < a ? y / a * RPT_PI : RPT_PI + (y - a) / (1.0f - a) * RPT_PI;
+  float sin_phi, cos_phi;
+  sincosf(phi, &sin_phi, &cos_phi);
+  float p1 = r * cos_phi;
+  float p2 = r * sin_phi * (y < a ? 1.0f : v.z);
+  float value = 1.0f - p1 * p1 - p2 * p2;
+  float3 n = p1 * t1 + p2 * t2 + sqrtf(fmaxf(value, 0.0f)) * v;
+  return normalized(f3(alpha * n.x, alpha * n.y, fmaxf(n.z, 0.0f)));
+}
+__device__ __forceinline__ float3 ggx_sample_wh(float alpha, float3 wi, float x, float y) {  // ggx.rs:171-180
+  bool flip = wi.z < 0.0f;
+  float3 wh = ggx_sample_vndf(alpha, flip ? -wi : wi, x, y);
+  return flip ? -wh : wh;
+}
+struct GgxParams {
+  float alpha, eta_inner, eta_outer, kappa;
+  bool metallic;
+};
+__device__ __forceinline__ float ggx_reflectance(const GgxParams &g, float c) {  // ggx.rs:221-227
+  return g.metallic ? fresnel_conductor(g.eta_outer, g.eta_inner, g.kappa, c) : fresnel_dielectric(g.eta_outer, g.eta_inner, c);
+}
+__device__ __forceinline__ float ggx_reflectance_probability(const GgxParams &g, float c) {  // ggx.rs:229-242
+  return g.metallic ? 1.0f : clampf(ggx_reflectance(g, c), 0.0f, 1.0f);
+}
+__device__ __forceinline__ float ggx_eta_rel(const GgxParams &g, float3 wi) {  // ggx.rs:243-252
+  return wi.z < 0.0f ? g.eta_outer / g.eta_inner : g.eta_inner / g.eta_outer;
+}
+// reflection lobe terms (ggx.rs:286-303 / 462-473)
+__device__ __forceinline__ void ggx_reflect_terms(const GgxParams &g, float3 wi, float3 wo, float3 wh, float gcos, float ndotv, float &glossy,
+                                                  float &glossy_pdf) {
+  float refl = ggx_reflectance(g, ndotv);
+  float d = ggx_d(g.alpha, wh);
+  float gg = ggx_g(g.alpha, wi, wo);
+  glossy = refl * (0.25f / gcos) * d * gg;
+  glossy_pdf = fabsf(ndotv) == 0.0f ? 0.0f : ggx_vnpdf(g.alpha, wi, wh) * 0.25f / fabsf(ndotv);
+}
+// transmission lobe terms, TransportMode::Importance (ggx.rs:318-368 / 488-537)
+__device__ __forceinline__ void ggx_transmit_terms(const GgxParams &g, float3 wi, float3 wo, float3 wh, float gcos, float &transmission,
+                                                   float &transmission_pdf) {
+  float eta_rel = ggx_eta_rel(g, wi);
+  float gg = ggx_g(g.alpha, wi, wo);
+  float partial = ggx_vnpdf_no_d(g.alpha, wi, wh);
+  float ndotv = dot(wi, wh), ndotl = dot(wo, wh);
+  float sqrt_denom = ndotv + eta_rel * ndotl;
+  float eta_rel2 = eta_rel * eta_rel;
+  float dwh_dwo1 = ndotl / (sqrt_denom * sqrt_denom);
+  float dwh_dwo2 = eta_rel2 * dwh_dwo1;
+  dwh_dwo1 = dwh_dwo2;  // Importance mode (ggx.rs:517-519)
+  float d = ggx_d(g.alpha, wh);
+  float weight = d * gg * ndotv * dwh_dwo1 / gcos;
+  transmission_pdf = fabsf(d * partial * dwh_dwo2);
+  float inv_reflectance = 1.0f - ggx_reflectance(g, ndotv);
+  transmission = g.metallic ? 0.0f : inv_reflectance * fabsf(weight);
+}
+// GGX::bsdf (ggx.rs:256-400)
+__device__ __forceinline__ Bsdf ggx_bsdf(const GgxParams &g, float3 wi, float3 wo) {
+  wi = normalized(wi);
+  bool same_hemisphere = wi.z * wo.z > 0.0f;
+  float gcos = fabsf(wi.z * wo.z);
+  Bsdf r;
+  r.f = 0.0f;
+  r.pdf = 0.0f;
+  if (gcos == 0.0f) return r;
+  float glossy = 0.0f, transmission = 0.0f, glossy_pdf = 0.0f, transmission_pdf = 0.0f;
+  if (same_hemisphere) {
+    float3 wh = normalized(wo + wi);
+    if (wh.z < 0.0f) wh = -wh;
+    ggx_reflect_terms(g, wi, wo, wh, gcos, dot(wi, wh), glossy, glossy_pdf);
+  } else if (!g.metallic) {
+    float eta_rel = ggx_eta_rel(g, wi);
+    float3 wh = normalized(wi + eta_rel * wo);
+    if (wh.z < 0.0f) wh = -wh;
+    ggx_transmit_terms(g, wi, wo, wh, gcos, transmission, transmission_pdf);
+  }
+  float refl_prob = ggx_reflectance_probability(g, wi.z);  // evaluated at wi.z (reference quirk Q8)
+  r.f = glossy + transmission;
+  r.pdf = refl_prob * glossy_pdf + (1.0f - refl_prob) * transmission_pdf;
+  return r;
+}
+// GGX::generate_and_evaluate (ggx.rs:401-590)
+__device__ __forceinline__ Bsdf ggx_generate_and_evaluate(const GgxParams &g, float sx, float sy, float3 wi, float3 &wo) {
+  float3 wh = normalized(ggx_sample_wh(g.alpha, wi, sx, sy));
+  float refl_prob = ggx_reflectance_probability(g, dot(wh, wi));
+  bool did_reflect = false;
+  if (sx <= refl_prob) {  // the same sample.x that drove the VNDF radius (Q7)
+    did_reflect = true;
+    wo = ggx_reflect(wi, wh);
+  } else {
+    float eta_rel = 1.0f / ggx_eta_rel(g, wi);
+    if (!ggx_refract(wi, wh, eta_rel, wo)) {
+      did_reflect = true;
+      wo = ggx_reflect(wi, wh);
+    }
+  }
+  Bsdf r;
+  r.f = 0.0f;
+  r.pdf = 0.0f;
+  float gcos = fabsf(wi.z * wo.z);
+  if (gcos == 0.0f) return r;
+  float cos_i;
+  float glossy = 0.0f, transmission = 0.0f, glossy_pdf = 0.0f, transmission_pdf = 0.0f;
+  if (did_reflect) {
+    cos_i = dot(wi, wh);
+    ggx_reflect_terms(g, wi, wo, wh, gcos, cos_i, glossy, glossy_pdf);
+  } else {
+    if (wh.z < 0.0f) wh = -wh;
+    cos_i = dot(wi, wh);
+    ggx_transmit_terms(g, wi, wo, wh, gcos, transmission, transmission_pdf);
+  }
+  float rp = ggx_reflectance_probability(g, cos_i);
+  r.f = glossy + transmission;
+  r.pdf = rp * glossy_pdf + (1.0f - rp) * transmission_pdf;
+  return r;
+}
+__device__ __forceinline__ GgxParams ggx_params(const DevScene &S, const RptMaterial &m, float lambda) {
+  GgxParams g;
+  g.alpha = m.alpha;
+  g.eta_inner = curve_eval(S, m.curve_a, lambda);
+  g.eta_outer = curve_eval(S, m.curve_b, lambda);
+  g.metallic = m.metallic != 0;
+  g.kappa = g.metallic ? curve_eval(S, m.curve_c, lambda) : 0.0f;
+  return g;
+}
+
+// Diffuse-like albedo: Lambertian texture (lambertian.rs:26) or a light's bounce_color (diffuse_light.rs:39).
+__device__ __forceinline__ float diffuse_albedo(const DevScene &S, const RptMaterial &m, float lambda, float u, float v) {
+  if (m.type == RPT_MATERIAL_LAMBERTIAN) return fminf(texstack_eval(S, m.texstack, lambda, u, v), 1.0f);
+  return clampf(curve_eval(S, m.curve_a, lambda), 0.0f, 1.0f);
+}
+// MaterialEnum::emission (diffuse_light.rs:123-133, sharp_light.rs:138-150,202-204); 0 for non-lights.
+__device__ __forceinline__ float material_emission(const DevScene &S, const RptMaterial &m, float lambda, float3 wi) {
+  if (m.type != RPT_MATERIAL_DIFFUSE_LIGHT && m.type != RPT_MATERIAL_SHARP_LIGHT) return 0.0f;
+  float cosine = wi.z;
+  bool ok = (cosine > 0.0f && m.sidedness == RPT_SIDED_FORWARD) || (cosine < 0.0f && m.sidedness == RPT_SIDED_REVERSE) ||
+            m.sidedness == RPT_SIDED_DUAL;
+  if (!ok) return 0.0f;
+  float e = curve_eval(S, m.curve_b, lambda);
+  if (m.type == RPT_MATERIAL_DIFFUSE_LIGHT) return e / RPT_PI;
+  return e * ((m.sharpness + 1.0f) * powf(fabsf(wi.z), m.sharpness) / 2.0f / RPT_PI);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CurveWithCDF (Linear variant) — importance-map tables
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float nearest_curve_eval(const float *__restrict__ signal, uint32_t n, float x) {
+  // Curve::Linear{bounds (0,1), Nearest}::evaluate
+  if (x < 0.0f || x > 1.0f) return 0.0f;
+  float step = 1.0f / (float)n;
+  uint32_t index = (uint32_t)(x / step);
+  if (index >= n) index = n - 1;
+  float left = __ldg(signal + index);
+  if (index + 1 >= n) return left;
+  float t = (x - (float)index * step) / step;
+  return t < 0.5f ? left : __ldg(signal + index + 1);
+}
+__device__ __forceinline__ void nearest_cdf_sample(const float *__restrict__ pdf, const float *__restrict__ cdf, uint32_t n, float pdf_integral,
+                                                   float sample, float &x_out, float &pdf_out) {
+  float lower_cdf = 0.0f;  // cdf.evaluate(-0.0001) is out of bounds
+  float upper_cdf = nearest_curve_eval(cdf, n, 1.0f - 0.0001f);
+  float s = lower_cdf + sample * (upper_cdf - lower_cdf);
+  uint32_t lo = 0, hi = n;  // first index with cdf[i] >= s
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(cdf + mid) < s) lo = mid + 1; else hi = mid;
+  }
+  uint32_t index = lo;
+  float x;
+  if (index == 0) {
+    x = 0.0f;
+  } else {
+    if (index >= n) index = n - 1;
+    float left = ((float)index - 1.0f) * 1.0f / (float)n;
+    float right = (float)index * 1.0f / (float)n;
+    float v0 = __ldg(cdf + index - 1), v1 = __ldg(cdf + index);
+    float t = (s - v0) / (v1 - v0);
+    x = t < 0.5f ? left : right;
+  }
+  x_out = x;
+  pdf_out = nearest_curve_eval(pdf, n, x) / pdf_integral;
+}
+
+// ---------------------------------------------------------------------------------------------
+// environment (world/environment.rs)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool env_in_sun(const DevScene &S, float u, float v) {
+  float3 dir = uv_to_direction(u, v);
+  float c = dot(S.env_sun_dir, dir);
+  float s = sqrtf(1.0f - c * c);
+  return fabsf(s) < sinf(S.env_angular_diameter / 2.0f) && c > 0.0f;
+}
+__device__ __forceinline__ float env_emission(const DevScene &S, float u, float v, float lambda) {  // :56-98
+  if (S.env_kind == RPT_ENV_CONSTANT) return curve_eval(S, S.env_curve, lambda) * S.env_strength;
+  if (S.env_kind == RPT_ENV_SUN) return env_in_sun(S, u, v) ? curve_eval(S, S.env_curve, lambda) * S.env_strength : 0.0f;
+  float3 nd = xform_vec(S.env_rot_rev, uv_to_direction(u, v));
+  float uu, vv;
+  direction_to_uv(nd, uu, vv);
+  return texstack_eval(S, S.env_texstack, lambda, uu, vv) * S.env_strength;
+}
+__device__ __forceinline__ float env_pdf_for(const DevScene &S, float u, float v) {  // :198-258
+  if (S.env_kind == RPT_ENV_CONSTANT) return 1.0f / (4.0f * RPT_PI);
+  if (S.env_kind == RPT_ENV_SUN) return env_in_sun(S, u, v) ? 1.0f / (2.0f * RPT_PI * (1.0f - cosf(S.env_angular_diameter))) : 0.0f;
+  if (S.imap_rows == 0) return 1.0f / (4.0f * RPT_PI);
+  float3 nd = xform_vec(S.env_rot_rev, uv_to_direction(u, v));
+  float uu, vv;
+  direction_to_uv(nd, uu, vv);
+  float m = nearest_curve_eval(S.imap_m_pdf, S.imap_marginal_n, uu);
+  uint32_t row = (uint32_t)(clampf(uu, 0.0f, 1.0f - RPT_EPS) * (float)S.imap_rows);
+  float r = nearest_curve_eval(S.imap_row_pdf + (size_t)row * S.imap_cols, S.imap_cols, vv);
+  return m * r * (2.0f * RPT_PI * RPT_PI * sinf(RPT_PI * vv) + 0.001f) + 0.001f;
+}
+__device__ __forceinline__ void env_sample_uv(const DevScene &S, float sx, float sy, float &u, float &v, float &pdf) {  // :303-353
+  if (S.env_kind == RPT_ENV_SUN) {
+    float3 local_wo = f3(0, 0, 1) + sinf(S.env_angular_diameter / 2.0f) * random_in_unit_disk(sx, sy);
+    Frame f = frame_from_normal(S.env_sun_dir);
+    direction_to_uv(normalized(to_world(f, local_wo)), u, v);
+    pdf = 1.0f / (2.0f * RPT_PI * (1.0f - cosf(S.env_angular_diameter)));
+    return;
+  }
+  if (S.env_kind == RPT_ENV_CONSTANT || S.imap_rows == 0) {
+    u = sx;
+    v = sy;
+    pdf = 1.0f / (4.0f * RPT_PI);
+    return;
+  }
+  // ImportanceMap::sample_uv (importance_map.rs:325-357): sample.y -> row (u), sample.x -> column (v)
+  float uu, row_pdf, vv, col_pdf;
+  nearest_cdf_sample(S.imap_m_pdf, S.imap_m_cdf, S.imap_marginal_n, S.imap_marginal_integral, sy, uu, row_pdf);
+  uint32_t row = (uint32_t)(uu * (float)S.imap_rows);
+  if (row >= S.imap_rows) row = S.imap_rows - 1;
+  nearest_cdf_sample(S.imap_row_pdf + (size_t)row * S.imap_cols, S.imap_row_cdf + (size_t)row * S.imap_cols, S.imap_cols, 1.0f, sx, vv, col_pdf);
+  float3 nw = xform_vec(S.env_rot_fwd, uv_to_direction(uu, vv));
+  direction_to_uv(nw, u, v);
+  pdf = row_pdf * col_pdf * (2.0f * RPT_PI * RPT_PI * sinf(RPT_PI * v) + 0.001f) + 0.001f;
+}

@@ -1,0 +1,1194 @@
+// rpt_kernels.cu — the wavefront PT pipeline (sm_100a) and the C ABI of include/rpt.h.
+//
+// Pipeline per wave of N = width*height*spp_chunk camera samples (reference pt.rs:397-615 unrolled
+// into a bounce-synchronous wavefront):
+//   k_raygen            : film jitter, wavelength, thin-lens camera ray            -> path queue
+//   per bounce b:
+//     k_trace           : two-level BVH closest hit, sorts paths by material class  -> hit records + class lists
+//     k_shade_miss      : environment vertex: emission * MIS                         (pt.rs:487-511)
+//     k_shade_surface<> : one launch per material class: light-hit MIS, NEE sample generation,
+//                         BSDF sampling, russian roulette                            -> next path queue + shadow queue
+//     k_shadow          : NEE visibility (closest hit for lights, any hit for env)  -> per-sample energy
+//   k_film              : energy * (x_bar, y_bar, z_bar)(lambda) summed per pixel   -> XYZ film
+// Queues are compacted with warp ballot / popc and one atomic per warp per queue; queue sizes stay
+// on the device, every kernel is a persistent grid-stride launch, so a wave needs no host sync.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rpt_bvh.h"
+#include "rpt_device.cuh"
+
+#ifdef RPT_DEBUG
+// debug builds only (make debug): kernel printf for one slot, selected with rpt_debug_set_slot()
+__device__ uint32_t d_debug_slot = 0xFFFFFFFFu;
+#define RPT_DEBUG_SLOT d_debug_slot
+extern "C" int rpt_debug_set_slot(uint32_t slot) { return cudaMemcpyToSymbol(d_debug_slot, &slot, sizeof(slot)) == cudaSuccess ? 0 : 1; }
+#endif
+
+namespace {
+
+thread_local std::string g_error;
+int fail(const std::string &msg) {
+  g_error = msg;
+  return 1;
+}
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// queue records
+// ---------------------------------------------------------------------------------------------
+// Path record, 64 B = 4 x float4, written contiguously by the producer (coalesced 128-bit stores).
+//   r0 = prev.point.xyz, beta                 (throughput before this segment's vertex)
+//   r1 = prev.normal.xyz, prev.pdf_forward    (camera vertex: ray direction, 100; pt.rs:436,441)
+//   r2 = ray direction.xyz, lambda
+//   r3 = slot (bits), offset sign (0 for the camera ray, else signum(wo.z)), unused, unused
+// The ray origin is derived exactly as the reference derives it: prev.point + prev.normal*0.001*sign
+// (integrator/utils.rs:326-329).
+struct __align__(16) PathRec {
+  float4 r0, r1, r2, r3;
+};
+struct __align__(16) HitRec {
+  float t;
+  uint32_t inst, prim, pad;
+};
+
+enum : uint32_t { Q_PATHS = 0, Q_MISS = 1, Q_DIFFUSE = 2, Q_GGX = 3, Q_SHADOW = 4, Q_NAN = 5, Q_SHADOW_REF = 6, Q_COUNT = 8 };
+#define RPT_MAX_BOUNCES 64
+
+struct RenderCtx {
+  uint32_t width, height, wh;
+  uint32_t n_slots;        // slots in this wave
+  uint32_t sample_base;    // global sample index of slot 0's sample
+  uint32_t min_bounces, max_bounces, light_samples, only_direct;
+  float lambda_lo, lambda_hi;
+  uint64_t seed;
+  RptCamera cam;
+};
+
+struct WaveBuffers {
+  PathRec *paths[2];
+  HitRec *hits;
+  uint32_t *q_miss, *q_diffuse, *q_ggx;
+  float4 *sh_a, *sh_b;  // shadow records: (origin.xyz, pre-contribution), (dir.xyz, lambda)
+  uint32_t *sh_c;       // slot | kind << 31 (1 = environment any-hit)
+  float *acc;           // per-slot energy (pt.rs `sum.energy`)
+  uint32_t *counts;     // [RPT_MAX_BOUNCES + 1][Q_COUNT]
+};
+
+__device__ __forceinline__ float3 rec_origin(const PathRec &r) {
+  float3 p = f3(r.r0), n = f3(r.r1);
+  return p + (n * RPT_NORMAL_OFFSET) * r.r3.y;
+}
+
+// warp-aggregated append: returns this lane's index in the queue, or RPT_NONE if !pred.
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
+  uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
+  if (mask == 0) return RPT_NONE;
+  uint32_t lane = threadIdx.x & 31u;
+  uint32_t leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(mask));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  return pred ? base + __popc(mask & ((1u << lane) - 1u)) : RPT_NONE;
+}
+// variable-count variant: each lane reserves `n` consecutive entries.
+__device__ __forceinline__ uint32_t warp_append_n(uint32_t *counter, uint32_t n) {
+  uint32_t lane = threadIdx.x & 31u;
+  uint32_t incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (uint32_t)o) incl += v;
+  }
+  uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  uint32_t base = 0;
+  if (total == 0) return 0;
+  if (lane == 31) base = atomicAdd(counter, total);
+  base = __shfl_sync(0xFFFFFFFFu, base, 31);
+  return base + incl - n;
+}
+
+#define TRACE_THREADS 128
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raygen(DevScene S, RenderCtx R, PathRec *__restrict__ out, uint32_t *__restrict__ counts) {
+  uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < R.n_slots; slot += stride) {
+    uint32_t pixel = slot % R.wh, sample = R.sample_base + slot / R.wh;
+    uint32_t px = pixel % R.width, py = pixel / R.width;
+    RptRand4 s0 = rpt_philox(R.seed, pixel, sample, 0);
+    RptRand4 s1 = rpt_philox(R.seed, pixel, sample, 1);
+    // box filter (tiled.rs:372-375), wavelength (pt.rs:406), film clamp (pt.rs:411-414)
+    float cu = ((float)px + s0.x) / (float)R.width, cv = ((float)py + s0.y) / (float)R.height;
+    float lambda = R.lambda_lo + s0.z * (R.lambda_hi - R.lambda_lo);
+    float fu = clampf(cu, 0.0f, 1.0f - RPT_EPS), fv = clampf(cv, 0.0f, 1.0f - RPT_EPS);
+    // ProjectiveCamera::get_ray (camera/projective_camera.rs:101-120)
+    float3 vec = random_in_unit_disk(s1.x, s1.y);
+    float3 rd = R.cam.aperture_diameter * vec;
+    float3 cu3 = f3(R.cam.u[0], R.cam.u[1], R.cam.u[2]), cv3 = f3(R.cam.v[0], R.cam.v[1], R.cam.v[2]);
+    float3 origin = f3(R.cam.origin[0], R.cam.origin[1], R.cam.origin[2]) + (cu3 * rd.x + cv3 * rd.y);
+    float3 pop = f3(R.cam.lower_left[0], R.cam.lower_left[1], R.cam.lower_left[2]) +
+                 fu * f3(R.cam.horizontal[0], R.cam.horizontal[1], R.cam.horizontal[2]) +
+                 fv * f3(R.cam.vertical[0], R.cam.vertical[1], R.cam.vertical[2]);
+    float3 dir = normalized(pop - origin);
+    PathRec r;
+    r.r0 = make_float4(origin.x, origin.y, origin.z, 1.0f);
+    r.r1 = make_float4(dir.x, dir.y, dir.z, 100.0f);
+    r.r2 = make_float4(dir.x, dir.y, dir.z, lambda);
+    r.r3 = make_float4(__uint_as_float(slot), 0.0f, 0.0f, 0.0f);
+    out[slot] = r;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[Q_PATHS] = R.n_slots;
+}
+
+__device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t material) {
+  return S.materials[RPT_MAT_INDEX(material)].type == RPT_MATERIAL_GGX ? Q_GGX : Q_DIFFUSE;
+}
+
+// Closest-hit traversal of the path queue; appends each path to the list of its vertex's class.
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
+                                                         uint32_t *__restrict__ q_miss, uint32_t *__restrict__ q_diffuse,
+                                                         uint32_t *__restrict__ q_ggx, uint32_t *__restrict__ counts) {
+  __shared__ int s_stack[RPT_STACK_SIZE * TRACE_THREADS];
+  const uint32_t n = counts[Q_PATHS];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t n_round = (n + 31u) & ~31u;  // keep whole warps in the loop for the ballots
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    bool active = i < n;
+    uint32_t cls = RPT_NONE;
+    if (active) {
+      const float4 *rp = reinterpret_cast<const float4 *>(paths + i);
+      PathRec r;
+      r.r0 = __ldg(rp);
+      r.r1 = __ldg(rp + 1);
+      r.r2 = __ldg(rp + 2);
+      r.r3 = __ldg(rp + 3);
+      float3 o = rec_origin(r), d = f3(r.r2);
+      TraceHit th;
+      bool hit = trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th);
+      HitRec h;
+      h.t = th.t;
+      h.inst = th.inst;
+      h.prim = th.prim;
+      h.pad = 0;
+      hits[i] = h;
+      if (!hit) {
+        cls = Q_MISS;
+      } else {
+        const DevInstance &I = S.instances[th.inst];
+        uint32_t mat = I.material;
+        if (mat == RPT_NONE) {
+          mat = RPT_MAT_PACK(RPT_MAT_TAG_MATERIAL, 0);
+          if ((I.flags & DI_KIND_MASK) == RPT_AGG_MESH) mat = __float_as_uint(__ldg(S.tri_verts + 3 * (size_t)(I.tri_base + th.prim)).w);
+        }
+        cls = material_class(S, mat);
+      }
+    }
+    uint32_t k;
+    k = warp_append(counts + Q_MISS, cls == Q_MISS);
+    if (cls == Q_MISS) q_miss[k] = i;
+    k = warp_append(counts + Q_DIFFUSE, cls == Q_DIFFUSE);
+    if (cls == Q_DIFFUSE) q_diffuse[k] = i;
+    k = warp_append(counts + Q_GGX, cls == Q_GGX);
+    if (cls == Q_GGX) q_ggx[k] = i;
+  }
+}
+
+// Environment vertex (integrator/utils.rs:344-373 + pt.rs:487-511).
+__global__ void __launch_bounds__(256) k_shade_miss(DevScene S, const PathRec *__restrict__ paths, const uint32_t *__restrict__ queue,
+                                                    const uint32_t *__restrict__ counts, float *__restrict__ acc) {
+  const uint32_t n = counts[Q_MISS];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t idx = queue[i];
+    const float4 *rp = reinterpret_cast<const float4 *>(paths + idx);
+    float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+    float3 wo = f3(r2);
+    float lambda = r2.w, beta = r0.w, pdf_fwd = r1.w;
+    float u, v;
+    direction_to_uv(wo, u, v);
+    float emission = env_emission(S, u, v, lambda);
+    float cos_i = fabsf(dot(f3(r1), wo));
+    float nee_psa_pdf = env_pdf_for(S, u, v) / fabsf(cos_i);
+    float bsdf_psa_pdf = pdf_fwd / fabsf(cos_i);
+    float weight = power_heuristic(bsdf_psa_pdf, nee_psa_pdf);
+    float c = weight * beta * emission;
+    if (c != 0.0f) atomicAdd(acc + __float_as_uint(r3.x), c);
+  }
+}
+
+// One walk vertex of a material class: light-hit MIS (pt.rs:512-561), NEE generation
+// (pt.rs:562-604,333-393,146-219,224-331), BSDF sampling + russian roulette (integrator/utils.rs:214-329).
+template <uint32_t CLASS>
+__global__ void __launch_bounds__(128) k_shade_surface(DevScene S, RenderCtx R, uint32_t bounce, const PathRec *__restrict__ paths,
+                                                       const HitRec *__restrict__ hits, const uint32_t *__restrict__ queue,
+                                                       uint32_t *__restrict__ counts, uint32_t *__restrict__ next_counts,
+                                                       PathRec *__restrict__ out, float4 *__restrict__ sh_a, float4 *__restrict__ sh_b,
+                                                       uint32_t *__restrict__ sh_c, float *__restrict__ acc) {
+  const uint32_t n = counts[CLASS];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t n_round = (n + 31u) & ~31u;
+  const uint32_t L = R.light_samples;
+  const uint32_t max_bounces = R.only_direct ? 1u : R.max_bounces;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    bool active = i < n;
+    bool continues = false, do_nee = false;
+    PathRec nr;
+    uint32_t n_sh_ref = 0;
+    // state shared between the vertex evaluation and the warp-uniform NEE loop below
+    SurfaceHit sh;
+    Frame frame;
+    float3 wi_nee = f3(0, 0, 1);
+    float beta = 0.0f, lambda = 0.0f, albedo = 0.0f;
+    uint32_t slot = 0, pixel = 0, sample = 0;
+    GgxParams gp;
+    gp.alpha = 1.0f;
+    gp.eta_inner = gp.eta_outer = 1.0f;
+    gp.kappa = 0.0f;
+    gp.metallic = false;
+    if (active) {
+      uint32_t idx = queue[i];
+      const float4 *rp = reinterpret_cast<const float4 *>(paths + idx);
+      PathRec r;
+      r.r0 = __ldg(rp);
+      r.r1 = __ldg(rp + 1);
+      r.r2 = __ldg(rp + 2);
+      r.r3 = __ldg(rp + 3);
+      HitRec hr = hits[idx];
+      TraceHit th;
+      th.t = hr.t;
+      th.inst = hr.inst;
+      th.prim = hr.prim;
+      float3 prev_p = f3(r.r0), prev_n = f3(r.r1), d = f3(r.r2);
+      float prev_pdf = r.r1.w;
+      beta = r.r0.w;
+      lambda = r.r2.w;
+      slot = __float_as_uint(r.r3.x);
+      float3 o = rec_origin(r);
+      reconstruct_hit(S, o, d, th, sh);
+      frame = frame_from_normal(sh.n);
+      float3 wi = normalized(to_local(frame, -d));  // integrator/utils.rs:175-176
+      const RptMaterial m = S.materials[RPT_MAT_INDEX(sh.material)];
+      pixel = slot % R.wh;
+      sample = R.sample_base + slot / R.wh;
+      RptRand4 s = rpt_philox(R.seed, pixel, sample, rpt_block_bsdf(bounce, L));
+
+      // ---- generate_and_evaluate
+      float3 wo;
+      float f, pdf;
+      if (CLASS == Q_GGX) {
+        gp = ggx_params(S, m, lambda);
+        Bsdf b = ggx_generate_and_evaluate(gp, s.x, s.y, wi, wo);
+        f = b.f;
+        pdf = b.pdf;
+      } else {
+        albedo = diffuse_albedo(S, m, lambda, sh.u, sh.v);
+        wo = random_cosine_direction(s.x, s.y) * signumf(wi.z);
+        f = albedo / RPT_PI;
+        pdf = fabsf(wo.z) / RPT_PI;
+      }
+#ifdef RPT_DEBUG
+      if (slot == RPT_DEBUG_SLOT)
+        printf("[shade b%u cls%u] p=(%.7g %.7g %.7g) n=(%.7g %.7g %.7g) mat=%u beta=%.7g prev_pdf=%.7g f=%.7g pdf=%.7g wo=(%.7g %.7g %.7g) wi=(%.7g %.7g %.7g) s=(%.7g %.7g %.7g) albedo=%.7g inst=%u prim=%u t=%.7g\n",
+               bounce, CLASS, sh.p.x, sh.p.y, sh.p.z, sh.n.x, sh.n.y, sh.n.z, sh.material, beta, prev_pdf, f, pdf, wo.x, wo.y, wo.z, wi.x, wi.y, wi.z, s.x, s.y, s.z, albedo, th.inst, th.prim, th.t);
+#endif
+      if (pdf != pdf) {
+        // pdf NaN: the walk breaks BEFORE pushing the vertex (integrator/utils.rs:261-263)
+        atomicAdd(counts + Q_NAN, 1u);
+      } else {
+        // ---- the vertex exists: its contribution (second loop of pt.rs:481-613)
+        if (RPT_MAT_IS_LIGHT(sh.material)) {
+          float emission = material_emission(S, m, lambda, wi);
+          if (emission > 0.0f) {
+            float c = 0.0f;
+            if (L == 0 || bounce == 0) {
+              c = beta * emission;
+            } else if (!R.only_direct) {
+              float3 nee_direction = normalized(sh.p - prev_p);
+              float hyp = instance_psa_pdf(S.instances[th.inst], dot(prev_n, nee_direction), dot(sh.n, nee_direction), prev_p, sh.p);
+              c = power_heuristic(prev_pdf, hyp) * beta * emission;
+            }
+#ifdef RPT_DEBUG
+            if (slot == RPT_DEBUG_SLOT) printf("[emit b%u] emission=%.7g c=%.7g\n", bounce, emission, c);
+#endif
+            if (c != 0.0f) atomicAdd(acc + slot, c);
+          }
+        } else if (L > 0) {
+          do_nee = true;
+          wi_nee = to_local(frame, normalized(prev_p - sh.p));  // pt.rs:565-569
+        }
+        // ---- continue the walk (integrator/utils.rs:266-329)
+        float cos_o = fabsf(wo.z);
+        float rr = bounce >= R.min_bounces ? fminf(f / pdf, 1.0f) : 1.0f;
+        float pdf_forward = pdf * (rr / cos_o);
+        float nbeta = beta * (f / pdf_forward);
+        if (pdf_forward == 0.0f) nbeta = 0.0f;
+        if (nbeta != 0.0f && !(s.z > rr) && bounce + 1 < max_bounces) {
+          float3 nd = normalized(to_world(frame, wo));
+          nr.r0 = make_float4(sh.p.x, sh.p.y, sh.p.z, nbeta);
+          nr.r1 = make_float4(sh.n.x, sh.n.y, sh.n.z, pdf_forward);
+          nr.r2 = make_float4(nd.x, nd.y, nd.z, lambda);
+          nr.r3 = make_float4(__uint_as_float(slot), signumf(wo.z), 0.0f, 0.0f);
+          continues = true;
+        }
+      }
+    }
+    // ---- next path queue: one atomic per warp
+    uint32_t k = warp_append(next_counts + Q_PATHS, continues);
+    if (continues) out[k] = nr;
+
+    // ---- NEE: warp-uniform loop over the light samples; every iteration compacts the lanes that
+    // produced a shadow ray into the shadow queue with one atomic (estimate_direct_illumination_with_loop).
+    if (__any_sync(0xFFFFFFFFu, do_nee)) {
+      float inv_l = 1.0f / (float)L;
+      for (uint32_t ls = 0; ls < L; ++ls) {
+        bool has = false;
+        float4 a = make_float4(0, 0, 0, 0), b4 = make_float4(0, 0, 0, 0);
+        uint32_t c = 0;
+        if (do_nee) {
+          RptRand4 sn = rpt_philox(R.seed, pixel, sample, rpt_block_nee(bounce, L, ls));
+          float pick;
+          bool sample_world = choose(sn.x, S.p_env, pick);  // pt.rs:350-353
+          float3 dir = f3(0, 0, 1);
+          float light_pdf = 0.0f, emission = 1.0f;
+          bool valid = true;
+          if (sample_world) {
+            float eu, ev;
+            env_sample_uv(S, sn.y, sn.z, eu, ev, light_pdf);
+            dir = uv_to_direction(eu, ev);
+            emission = env_emission(S, eu, ev, lambda);
+          } else {
+            valid = S.num_lights > 0;
+            if (valid) {
+              uint32_t li = (uint32_t)clampf((float)S.num_lights * pick, 0.0f, (float)S.num_lights - 1.0f);  // world/mod.rs:109
+              instance_sample(S.instances[S.lights[li]], sn.y, sn.z, sh.p, dir, light_pdf);
+              light_pdf = light_pdf * (1.0f / (float)S.num_lights);
+              valid = light_pdf != 0.0f;  // pt.rs:151-153
+            }
+          }
+          float3 local_wo = to_local(frame, dir);
+          if (sample_world && local_wo.z <= 0.0f) valid = false;  // pt.rs:245-247
+          if (valid) {
+            Bsdf bs;
+            if (CLASS == Q_GGX) {
+              bs = ggx_bsdf(gp, wi_nee, local_wo);
+            } else {  // lambertian.rs:16-32 / diffuse_light.rs:29-45
+              bool same = local_wo.z * wi_nee.z > 0.0f;
+              bs.f = same ? albedo / RPT_PI : 0.0f;
+              bs.pdf = same ? fabsf(local_wo.z) / RPT_PI : 0.0f;
+            }
+            n_sh_ref++;  // the reference traces (and counts) this ray whatever its weight
+            float weight = R.only_direct ? 1.0f : power_heuristic_generic(light_pdf, bs.pdf);
+            float pre;
+            float3 so;
+            if (sample_world) {
+              pre = beta * weight * bs.f * emission * fabsf(local_wo.z) * (1.0f / light_pdf) * inv_l;  // pt.rs:313-318
+              so = sh.p + (sh.n * RPT_NORMAL_OFFSET) * signumf(dir.z);  // WORLD z (quirk Q12, pt.rs:256)
+              c = slot | 0x80000000u;
+            } else {
+              pre = bs.f * beta * fabsf(local_wo.z) * weight / light_pdf * inv_l;  // pt.rs:196-202 minus the light-side terms
+              so = sh.p + (sh.n * RPT_NORMAL_OFFSET) * signumf(local_wo.z);  // pt.rs:171-174
+              c = slot;
+            }
+#ifdef RPT_DEBUG
+            if (slot == RPT_DEBUG_SLOT)
+              printf("[nee b%u k%u] world=%d dir=(%.7g %.7g %.7g) light_pdf=%.7g bsdf f=%.7g pdf=%.7g weight=%.7g pre=%.7g local_wo.z=%.7g\n", bounce, ls,
+                     (int)sample_world, dir.x, dir.y, dir.z, light_pdf, bs.f, bs.pdf, weight, pre, local_wo.z);
+#endif
+            if (pre != 0.0f) {  // a zero pre-factor cannot contribute: skip the visibility query
+              has = true;
+              a = make_float4(so.x, so.y, so.z, pre);
+              b4 = make_float4(dir.x, dir.y, dir.z, lambda);
+            }
+          }
+        }
+        uint32_t q = warp_append(counts + Q_SHADOW, has);
+        if (has) {
+          sh_a[q] = a;
+          sh_b[q] = b4;
+          sh_c[q] = c;
+        }
+      }
+      // reference-definition shadow-ray counter (pt.rs:176,252)
+      uint32_t tot = n_sh_ref;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+      if ((threadIdx.x & 31u) == 0 && tot) atomicAdd(counts + Q_SHADOW_REF, tot);
+    }
+  }
+}
+
+// NEE visibility. Light samples: closest hit, accepted when ANY light-material surface is hit, whose own
+// emission is used (pt.rs:177-218, F9). Environment samples: any hit kills the sample (pt.rs:254-263).
+__global__ void __launch_bounds__(TRACE_THREADS) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
+                                                          const uint32_t *__restrict__ sh_c, const uint32_t *__restrict__ counts,
+                                                          float *__restrict__ acc) {
+  __shared__ int s_stack[RPT_STACK_SIZE * TRACE_THREADS];
+  const uint32_t n = counts[Q_SHADOW];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float4 a = __ldg(sh_a + i), b = __ldg(sh_b + i);
+    uint32_t c = __ldg(sh_c + i);
+    float3 o = f3(a), d = f3(b);
+    float pre = a.w, lambda = b.w;
+    uint32_t slot = c & 0x7FFFFFFFu;
+    TraceHit th;
+    if (c & 0x80000000u) {
+      if (!trace_ray<true>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th)) atomicAdd(acc + slot, pre);
+    } else {
+      if (trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th)) {
+        SurfaceHit sh;
+        reconstruct_hit(S, o, d, th, sh);
+        if (RPT_MAT_IS_LIGHT(sh.material)) {
+          Frame lf = frame_from_normal(sh.n);
+          float3 lwi = to_local(lf, -d);
+          float le = material_emission(S, S.materials[RPT_MAT_INDEX(sh.material)], lambda, lwi);
+          float v = pre * fabsf(lwi.z) * le;
+#ifdef RPT_DEBUG
+          if (slot == RPT_DEBUG_SLOT) printf("[shadow] hit inst=%u prim=%u t=%.7g le=%.7g lwi.z=%.7g pre=%.7g -> %.7g\n", th.inst, th.prim, th.t, le, lwi.z, pre, v);
+#endif
+          if (v != 0.0f) atomicAdd(acc + slot, v);
+        }
+      }
+    }
+  }
+}
+
+// XYZColor::from(SingleWavelength) (pt.rs:614) + per-pixel accumulation (tiled.rs:390).
+// One thread per pixel sums that pixel's samples of the wave: coalesced, no atomics. The CIE tables are
+// staged in shared memory once per CTA.
+__global__ void __launch_bounds__(256) k_film(DevScene S, RenderCtx R, const float *__restrict__ acc, float4 *__restrict__ film) {
+  extern __shared__ float s_cie[];
+  for (uint32_t i = threadIdx.x; i < 3 * S.num_lambda; i += blockDim.x) s_cie[i] = S.cie_lut[i];
+  __syncthreads();
+  uint32_t spp = R.n_slots / R.wh;
+  uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < R.wh; pixel += stride) {
+    float X = 0.0f, Y = 0.0f, Z = 0.0f;
+    for (uint32_t s = 0; s < spp; ++s) {
+      float e = acc[(size_t)s * R.wh + pixel];
+      if (e == 0.0f) continue;
+      RptRand4 s0 = rpt_philox(R.seed, pixel, R.sample_base + s, 0);
+      float lambda = R.lambda_lo + s0.z * (R.lambda_hi - R.lambda_lo);
+      float x = (lambda - S.lut_lo) / (S.lut_hi - S.lut_lo) * (float)(S.num_lambda - 1);
+      x = clampf(x, 0.0f, (float)(S.num_lambda - 1));
+      uint32_t j = (uint32_t)x;
+      if (j > S.num_lambda - 2) j = S.num_lambda - 2;
+      float t = x - (float)j;
+      const float *cx = s_cie, *cy = s_cie + S.num_lambda, *cz = s_cie + 2 * S.num_lambda;
+      X += e * __fadd_rn(cx[j], __fmul_rn(t, __fsub_rn(cx[j + 1], cx[j])));
+      Y += e * __fadd_rn(cy[j], __fmul_rn(t, __fsub_rn(cy[j + 1], cy[j])));
+      Z += e * __fadd_rn(cz[j], __fmul_rn(t, __fsub_rn(cz[j + 1], cz[j])));
+    }
+    float4 f = film[pixel];
+    f.x += X;
+    f.y += Y;
+    f.z += Z;
+    film[pixel] = f;
+  }
+}
+
+__global__ void k_scale(float4 *film, uint64_t n, float s) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float4 f = film[i];
+    f.x *= s;
+    f.y *= s;
+    f.z *= s;
+    f.w = 0.0f;
+    film[i] = f;
+  }
+}
+
+// generic closest-hit query of host-provided rays (rpt_trace_rays)
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32_t n, const float *__restrict__ o, const float *__restrict__ d,
+                                                              const float *__restrict__ tmax, HitRec *__restrict__ hits) {
+  __shared__ int s_stack[RPT_STACK_SIZE * TRACE_THREADS];
+  uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    TraceHit th;
+    trace_ray<false>(S, f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), tmax[i], s_stack + threadIdx.x,
+                     TRACE_THREADS, th);
+    HitRec h;
+    h.t = th.t;
+    h.inst = th.inst;
+    h.prim = th.prim;
+    h.pad = 0;
+    hits[i] = h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: scene upload + wave driver
+// ---------------------------------------------------------------------------------------------
+enum KernelId { K_RAYGEN, K_TRACE, K_SHADE_MISS, K_SHADE_DIFFUSE, K_SHADE_GGX, K_SHADOW, K_FILM, K_NUM };
+const char *kKernelNames[K_NUM] = {"k_raygen", "k_trace", "k_shade_miss", "k_shade_surface<diffuse>", "k_shade_surface<ggx>", "k_shadow", "k_film"};
+
+struct DeviceBuffers {
+  std::vector<void *> ptrs;
+  template <class T>
+  int upload(const T *host, size_t n, const T **out) {
+    *out = nullptr;
+    if (n == 0) return 0;
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
+    ptrs.push_back(p);
+    CUDA_TRY(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T *>(p);
+    return 0;
+  }
+  void release() {
+    for (void *p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+}  // namespace
+
+struct RptScene {
+  int device = 0;
+  int num_sms = 0;
+  DevScene dev{};
+  DeviceBuffers bufs;
+  std::vector<RptCamera> cameras;
+  RptSceneStats stats{};
+  cudaStream_t stream = nullptr;
+  // wave buffers (grown on demand, reused across calls)
+  WaveBuffers wave{};
+  size_t wave_slots = 0, wave_shadow = 0;
+  float4 *film = nullptr;
+  size_t film_pixels = 0;
+  // launch geometry
+  int grid[K_NUM] = {0};
+  // timing of the last render
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span {
+    int kernel;
+    size_t e0, e1;
+  };
+  std::vector<Span> spans;
+  float kernel_ms[K_NUM] = {0};
+  uint32_t kernel_launches[K_NUM] = {0};
+};
+
+namespace {
+
+void to3x4(const float *m16, float4 *out) {
+  for (int r = 0; r < 3; ++r) out[r] = make_float4(m16[4 * r], m16[4 * r + 1], m16[4 * r + 2], m16[4 * r + 3]);
+}
+rpt::Box box_of_points(const float *p, size_t n) {
+  rpt::Box b{{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}};
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) {
+      b.mn[k] = std::fmin(b.mn[k], p[3 * i + k]);
+      b.mx[k] = std::fmax(b.mx[k], p[3 * i + k]);
+    }
+  return b;
+}
+void shuffle3(const float in[3], uint32_t axis, float out[3]) {
+  if (axis == RPT_AXIS_X) {
+    out[0] = in[2]; out[1] = in[1]; out[2] = in[0];
+  } else if (axis == RPT_AXIS_Y) {
+    out[0] = in[0]; out[1] = in[2]; out[2] = in[1];
+  } else {
+    out[0] = in[0]; out[1] = in[1]; out[2] = in[2];
+  }
+}
+// Matrix4x4 * AABB over the 8 corners (aabb.rs:116-138)
+rpt::Box transform_box(const float *m, const rpt::Box &b) {
+  rpt::Box o{{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}};
+  for (int i = 0; i < 8; ++i) {
+    float p[3] = {(i & 1) ? b.mx[0] : b.mn[0], (i & 2) ? b.mx[1] : b.mn[1], (i & 4) ? b.mx[2] : b.mn[2]};
+    for (int r = 0; r < 3; ++r) {
+      float v = m[4 * r] * p[0] + m[4 * r + 1] * p[1] + m[4 * r + 2] * p[2] + m[4 * r + 3];
+      o.mn[r] = std::fmin(o.mn[r], v);
+      o.mx[r] = std::fmax(o.mx[r], v);
+    }
+  }
+  return o;
+}
+DevNode to_dev_node(const rpt::HostNode &h, int32_t node_offset) {
+  DevNode d;
+  d.lmin_lmaxx = make_float4(h.lmin[0], h.lmin[1], h.lmin[2], h.lmax[0]);
+  d.lmaxyz_rminxy = make_float4(h.lmax[1], h.lmax[2], h.rmin[0], h.rmin[1]);
+  d.rminz_rmax = make_float4(h.rmin[2], h.rmax[0], h.rmax[1], h.rmax[2]);
+  d.children = make_int4(h.left >= 0 ? h.left + node_offset : h.left, h.right >= 0 ? h.right + node_offset : h.right, 0, 0);
+  return d;
+}
+
+template <class K>
+int occupancy_grid(K kernel, int threads, size_t smem, int num_sms) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * num_sms;
+}
+
+int free_wave(RptScene *S) {
+  WaveBuffers &w = S->wave;
+  void *ptrs[] = {w.paths[0], w.paths[1], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.sh_a, w.sh_b, w.sh_c, w.acc, w.counts};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  w = WaveBuffers{};
+  S->wave_slots = S->wave_shadow = 0;
+  return 0;
+}
+
+int ensure_wave(RptScene *S, size_t slots, size_t shadow) {
+  if (slots <= S->wave_slots && shadow <= S->wave_shadow) return 0;
+  free_wave(S);
+  WaveBuffers &w = S->wave;
+  CUDA_TRY(cudaMalloc(&w.paths[0], slots * sizeof(PathRec)));
+  CUDA_TRY(cudaMalloc(&w.paths[1], slots * sizeof(PathRec)));
+  CUDA_TRY(cudaMalloc(&w.hits, slots * sizeof(HitRec)));
+  CUDA_TRY(cudaMalloc(&w.q_miss, slots * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.q_diffuse, slots * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.q_ggx, slots * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.sh_a, std::max<size_t>(shadow, 1) * sizeof(float4)));
+  CUDA_TRY(cudaMalloc(&w.sh_b, std::max<size_t>(shadow, 1) * sizeof(float4)));
+  CUDA_TRY(cudaMalloc(&w.sh_c, std::max<size_t>(shadow, 1) * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.acc, slots * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&w.counts, (RPT_MAX_BOUNCES + 1) * Q_COUNT * sizeof(uint32_t)));
+  S->wave_slots = slots;
+  S->wave_shadow = shadow;
+  return 0;
+}
+
+size_t bytes_per_slot(uint32_t light_samples) {
+  return 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t) + sizeof(float) + (size_t)light_samples * (2 * sizeof(float4) + sizeof(uint32_t));
+}
+
+struct Launcher {
+  RptScene *S;
+  cudaEvent_t next_event() {
+    if (S->ev_used == S->ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      S->ev_pool.push_back(e);
+    }
+    return S->ev_pool[S->ev_used++];
+  }
+  void begin(int kernel) {
+    size_t e0 = S->ev_used;
+    cudaEventRecord(next_event(), S->stream);
+    S->spans.push_back({kernel, e0, 0});
+  }
+  void end() {
+    size_t e1 = S->ev_used;
+    cudaEventRecord(next_event(), S->stream);
+    S->spans.back().e1 = e1;
+    S->kernel_launches[S->spans.back().kernel] += 1;
+  }
+};
+
+int validate(const RptScene *S, const RptRenderParams *P) {
+  if (!S || !P) return fail("null argument");
+  if (P->width == 0 || P->height == 0) return fail("empty film");
+  if (P->camera >= S->cameras.size()) return fail("camera index out of range");
+  if (P->max_bounces > RPT_MAX_BOUNCES) return fail("max_bounces exceeds RPT_MAX_BOUNCES (64)");
+  if (P->light_samples > 8) return fail("light_samples > 8 is not supported by the shade kernel's shadow-record staging");
+  if ((uint64_t)P->width * P->height >= (1ull << 31)) return fail("film too large");
+  return 0;
+}
+
+RenderCtx make_ctx(const RptScene *S, const RptRenderParams *P) {
+  RenderCtx R{};
+  R.width = P->width;
+  R.height = P->height;
+  R.wh = P->width * P->height;
+  R.min_bounces = P->min_bounces;
+  R.max_bounces = P->max_bounces;
+  R.light_samples = P->light_samples;
+  R.only_direct = P->only_direct;
+  R.lambda_lo = P->lambda_lo;
+  R.lambda_hi = P->lambda_hi;
+  R.seed = P->seed;
+  R.cam = S->cameras[P->camera];
+  return R;
+}
+
+// Renders P->spp samples per pixel into S->film (un-normalised sum). Fills counters.
+int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
+  if (int rc = validate(S, P)) return rc;
+  CUDA_TRY(cudaSetDevice(S->device));
+  const size_t wh = (size_t)P->width * P->height;
+  if (S->film_pixels != wh) {
+    if (S->film) cudaFree(S->film);
+    S->film = nullptr;
+    CUDA_TRY(cudaMalloc(&S->film, wh * sizeof(float4)));
+    S->film_pixels = wh;
+  }
+  CUDA_TRY(cudaMemsetAsync(S->film, 0, wh * sizeof(float4), S->stream));
+
+  // wave sizing: as many spp per wave as fit the memory budget and the 31-bit slot id
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  size_t held = S->wave_slots * bytes_per_slot(0) + S->wave_shadow * (2 * sizeof(float4) + sizeof(uint32_t));
+  size_t budget = std::min<size_t>((size_t)((free_b + held) * 0.5), (size_t)32 << 30);
+  size_t per_slot = bytes_per_slot(P->light_samples);
+  size_t max_slots = std::min<size_t>(budget / per_slot, (size_t)1 << 30);
+  uint32_t spp_chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(P->spp ? P->spp : 1, max_slots / wh));
+  if (wh > max_slots) return fail("film does not fit one wave");
+  size_t slots = wh * spp_chunk;
+  if (int rc = ensure_wave(S, slots, slots * P->light_samples)) return rc;
+
+  S->ev_used = 0;
+  S->spans.clear();
+  std::memset(S->kernel_ms, 0, sizeof(S->kernel_ms));
+  std::memset(S->kernel_launches, 0, sizeof(S->kernel_launches));
+  Launcher T{S};
+  RenderCtx R = make_ctx(S, P);
+  const uint32_t max_bounces = P->only_direct ? 1u : P->max_bounces;
+  WaveBuffers &w = S->wave;
+  std::vector<uint32_t> h_counts((RPT_MAX_BOUNCES + 1) * Q_COUNT);
+  RptCounters C{};
+  size_t film_smem = 3 * (size_t)S->dev.num_lambda * sizeof(float);
+
+  for (uint32_t done = 0; done < P->spp; done += spp_chunk) {
+    uint32_t chunk = std::min(spp_chunk, P->spp - done);
+    R.n_slots = (uint32_t)(wh * chunk);
+    R.sample_base = P->spp_offset + done;
+    CUDA_TRY(cudaMemsetAsync(w.counts, 0, h_counts.size() * sizeof(uint32_t), S->stream));
+    CUDA_TRY(cudaMemsetAsync(w.acc, 0, (size_t)R.n_slots * sizeof(float), S->stream));
+    T.begin(K_RAYGEN);
+    k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
+    T.end();
+    for (uint32_t b = 0; b < max_bounces; ++b) {
+      uint32_t *cb = w.counts + (size_t)b * Q_COUNT, *cn = w.counts + (size_t)(b + 1) * Q_COUNT;
+      PathRec *in = w.paths[b & 1], *out = w.paths[(b + 1) & 1];
+      T.begin(K_TRACE);
+      k_trace<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb);
+      T.end();
+      T.begin(K_SHADE_MISS);
+      k_shade_miss<<<S->grid[K_SHADE_MISS], 256, 0, S->stream>>>(S->dev, in, w.q_miss, cb, w.acc);
+      T.end();
+      T.begin(K_SHADE_DIFFUSE);
+      k_shade_surface<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], 128, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
+      T.end();
+      T.begin(K_SHADE_GGX);
+      k_shade_surface<Q_GGX><<<S->grid[K_SHADE_GGX], 128, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
+      T.end();
+      if (P->light_samples > 0) {
+        T.begin(K_SHADOW);
+        k_shadow<<<S->grid[K_SHADOW], TRACE_THREADS, 0, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc);
+        T.end();
+      }
+    }
+    T.begin(K_FILM);
+    k_film<<<S->grid[K_FILM], 256, film_smem, S->stream>>>(S->dev, R, w.acc, S->film);
+    T.end();
+    CUDA_TRY(cudaMemcpyAsync(h_counts.data(), w.counts, h_counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, S->stream));
+    CUDA_TRY(cudaStreamSynchronize(S->stream));
+    CUDA_TRY(cudaGetLastError());
+    // Profile counters (profile.rs:1-8) from the queue sizes
+    C.camera_rays += R.n_slots;
+    C.bounce_rays += R.n_slots;  // the camera vertex (pt.rs:465, integrator/utils.rs:375)
+    for (uint32_t b = 0; b < max_bounces; ++b) {
+      const uint32_t *c = &h_counts[(size_t)b * Q_COUNT];
+      C.segments += c[Q_PATHS];
+      C.true_rays += c[Q_PATHS] + c[Q_SHADOW];
+      C.env_hits += c[Q_MISS];
+      C.bounce_rays += c[Q_MISS] + c[Q_DIFFUSE] + c[Q_GGX] - c[Q_NAN];
+      C.shadow_rays += c[Q_SHADOW_REF];
+    }
+  }
+  for (auto &sp : S->spans) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, S->ev_pool[sp.e0], S->ev_pool[sp.e1]);
+    S->kernel_ms[sp.kernel] += ms;
+  }
+  for (int k = 0; k < K_NUM; ++k) C.kernel_launches += S->kernel_launches[k];
+  if (counters) *counters = C;
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *rpt_last_error(void) { return g_error.c_str(); }
+uint32_t rpt_abi_version(void) { return RPT_ABI_VERSION; }
+
+int rpt_device_count(int *count) {
+  if (!count) return fail("null argument");
+  CUDA_TRY(cudaGetDeviceCount(count));
+  return 0;
+}
+
+int rpt_scene_destroy(RptScene *S) {
+  if (!S) return 0;
+  cudaSetDevice(S->device);
+  free_wave(S);
+  if (S->film) cudaFree(S->film);
+  S->bufs.release();
+  for (cudaEvent_t e : S->ev_pool) cudaEventDestroy(e);
+  if (S->stream) cudaStreamDestroy(S->stream);
+  delete S;
+  return 0;
+}
+
+int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
+  if (!d || !out) return fail("null argument");
+  if (d->abi_version != RPT_ABI_VERSION) return fail("ABI version mismatch (include/rpt.h RPT_ABI_VERSION)");
+  if (d->num_instances == 0) return fail("scene has no instances");
+  if (d->num_lambda < 2) return fail("num_lambda must be >= 2");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("no such CUDA device (there is no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+  RptScene *S = new RptScene();
+  S->device = device;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  S->num_sms = prop.multiProcessorCount;
+  auto bail = [&](int rc) {
+    rpt_scene_destroy(S);
+    return rc;
+  };
+  if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
+
+  // ---- geometry: per-mesh BLAS, then the TLAS over instance boxes
+  std::vector<DevNode> nodes;
+  std::vector<float4> tri_verts, tri_normals;
+  struct MeshInfo {
+    int32_t root;
+    uint32_t tri_base;
+    rpt::Box box;
+    bool has_normals;
+    uint32_t depth;
+  };
+  std::vector<MeshInfo> minfo(d->num_meshes);
+  std::vector<std::vector<DevNode>> blas_nodes(d->num_meshes);
+  bool any_normals = false;
+  for (uint32_t m = 0; m < d->num_meshes; ++m) any_normals |= d->meshes[m].normals != nullptr;
+  uint32_t max_blas_depth = 0;
+  for (uint32_t m = 0; m < d->num_meshes; ++m) {
+    const RptMesh &M = d->meshes[m];
+    if (M.num_faces == 0) return bail(fail("mesh without faces"));
+    std::vector<rpt::Box> boxes(M.num_faces);
+    for (uint32_t t = 0; t < M.num_faces; ++t) {
+      float pts[9];
+      for (int k = 0; k < 3; ++k) {
+        uint32_t vi = M.indices[3 * t + k];
+        if (vi >= M.num_vertices) return bail(fail("mesh index out of range"));
+        std::memcpy(pts + 3 * k, M.vertices + 3 * (size_t)vi, 3 * sizeof(float));
+      }
+      boxes[t] = box_of_points(pts, 3);  // MeshTriangleRef::aabb (mesh.rs:57-64)
+    }
+    rpt::BuiltBvh bvh = rpt::build_bvh(boxes);
+    minfo[m].tri_base = (uint32_t)(tri_verts.size() / 3);
+    minfo[m].box = box_of_points(M.vertices, M.num_vertices);  // Mesh::new bounding box (mesh.rs:271-274)
+    minfo[m].has_normals = M.normals != nullptr;
+    minfo[m].root = bvh.root;  // relative; fixed up below
+    minfo[m].depth = bvh.max_depth;
+    max_blas_depth = std::max(max_blas_depth, bvh.max_depth);
+    blas_nodes[m].reserve(bvh.nodes.size());
+    for (auto &hn : bvh.nodes) blas_nodes[m].push_back(to_dev_node(hn, 0));
+    for (uint32_t t = 0; t < M.num_faces; ++t) {
+      uint32_t mat = M.face_material ? M.face_material[t] : RPT_MAT_PACK(RPT_MAT_TAG_MATERIAL, 0);
+      for (int k = 0; k < 3; ++k) {
+        const float *p = M.vertices + 3 * (size_t)M.indices[3 * t + k];
+        uint32_t wbits = k == 0 ? mat : (k == 1 ? bvh.order[t] : 0u);
+        float wf;
+        std::memcpy(&wf, &wbits, 4);
+        tri_verts.push_back(make_float4(p[0], p[1], p[2], wf));
+        if (any_normals) {
+          if (M.normals) {
+            const float *nn = M.normals + 3 * (size_t)M.indices[3 * t + k];
+            tri_normals.push_back(make_float4(nn[0], nn[1], nn[2], 0.0f));
+          } else {
+            tri_normals.push_back(make_float4(0, 0, 0, 0));
+          }
+        }
+      }
+    }
+    S->stats.triangles += M.num_faces;
+    S->stats.blas_nodes += bvh.nodes.size();
+  }
+
+  std::vector<rpt::Box> ibox(d->num_instances);
+  rpt::Box world{{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}};
+  for (uint32_t i = 0; i < d->num_instances; ++i) {
+    const RptInstance &I = d->instances[i];
+    rpt::Box b;
+    switch (I.kind) {
+      case RPT_AGG_RECT: {  // rect.rs:58-66
+        float half[3] = {I.size[0] / 2.0f, I.size[1] / 2.0f, 0.0001f}, v[3];
+        shuffle3(half, I.axis, v);
+        for (int k = 0; k < 3; ++k) {
+          b.mn[k] = std::fmin(I.origin[k] - v[k], I.origin[k] + v[k]);
+          b.mx[k] = std::fmax(I.origin[k] - v[k], I.origin[k] + v[k]);
+        }
+        break;
+      }
+      case RPT_AGG_SPHERE:
+        for (int k = 0; k < 3; ++k) {
+          b.mn[k] = I.origin[k] - I.size[0];
+          b.mx[k] = I.origin[k] + I.size[0];
+        }
+        break;
+      case RPT_AGG_DISK: {  // disk.rs:23-28 (half extent radius/2: reference quirk, kept)
+        float v[3] = {I.size[0] / 2.0f, I.size[0] / 2.0f, 0.001f};
+        for (int k = 0; k < 3; ++k) {
+          b.mn[k] = I.origin[k] - v[k];
+          b.mx[k] = I.origin[k] + v[k];
+        }
+        break;
+      }
+      case RPT_AGG_MESH:
+        if (I.mesh < 0 || (uint32_t)I.mesh >= d->num_meshes) return bail(fail("instance references a missing mesh"));
+        b = minfo[I.mesh].box;
+        break;
+      default: return bail(fail("unknown aggregate kind"));
+    }
+    if (I.has_transform) b = transform_box(I.forward, b);  // instance.rs:64-72
+    ibox[i] = b;
+    for (int k = 0; k < 3; ++k) {
+      world.mn[k] = std::fmin(world.mn[k], b.mn[k]);
+      world.mx[k] = std::fmax(world.mx[k], b.mx[k]);
+    }
+  }
+  rpt::BuiltBvh tlas = rpt::build_bvh(ibox);
+  if (tlas.max_depth + max_blas_depth + 4 > RPT_STACK_SIZE)
+    return bail(fail("BVH deeper than the traversal stack (RPT_STACK_SIZE)"));
+  for (auto &hn : tlas.nodes) nodes.push_back(to_dev_node(hn, 0));
+  S->stats.tlas_nodes = tlas.nodes.size();
+  std::vector<int32_t> mesh_root(d->num_meshes);
+  for (uint32_t m = 0; m < d->num_meshes; ++m) {
+    int32_t off = (int32_t)nodes.size();
+    for (DevNode n : blas_nodes[m]) {
+      if (n.children.x >= 0) n.children.x += off;
+      if (n.children.y >= 0) n.children.y += off;
+      nodes.push_back(n);
+    }
+    mesh_root[m] = minfo[m].root >= 0 ? minfo[m].root + off : minfo[m].root;
+  }
+
+  std::vector<DevInstance> insts(d->num_instances);
+  for (uint32_t i = 0; i < d->num_instances; ++i) {
+    const RptInstance &I = d->instances[i];
+    DevInstance &D = insts[i];
+    std::memset(&D, 0, sizeof(D));
+    to3x4(I.reverse, D.rev);
+    to3x4(I.forward, D.fwd);
+    D.origin_size0 = make_float4(I.origin[0], I.origin[1], I.origin[2], I.size[0]);
+    D.size1 = I.size[1];
+    D.flags = (I.kind & DI_KIND_MASK) | ((I.axis & 3u) << DI_AXIS_SHIFT) | (I.two_sided ? DI_TWO_SIDED : 0u) | (I.has_transform ? DI_HAS_TRANSFORM : 0u);
+    D.material = I.material;
+    D.order = tlas.order[i];
+    if (I.kind == RPT_AGG_MESH) {
+      D.blas_root = mesh_root[I.mesh];
+      D.tri_base = minfo[I.mesh].tri_base;
+      D.has_normals = minfo[I.mesh].has_normals;
+    }
+  }
+  for (uint32_t l = 0; l < d->num_lights; ++l) {
+    if (d->lights[l] >= d->num_instances) return bail(fail("light references a missing instance"));
+    if (d->instances[d->lights[l]].kind == RPT_AGG_MESH)
+      return bail(fail("mesh lights are unimplemented in the reference (src/geometry/mesh.rs:362-386 todo!())"));
+  }
+
+  DevScene &D = S->dev;
+  DeviceBuffers &B = S->bufs;
+  int rc = 0;
+  rc |= B.upload(nodes.data(), nodes.size(), &D.nodes);
+  rc |= B.upload(insts.data(), insts.size(), &D.instances);
+  rc |= B.upload(tri_verts.data(), tri_verts.size(), &D.tri_verts);
+  rc |= B.upload(tri_normals.data(), tri_normals.size(), &D.tri_normals);
+  rc |= B.upload(d->lights, d->num_lights, &D.lights);
+  rc |= B.upload(d->materials, d->num_materials, &D.materials);
+  rc |= B.upload(d->curve_lut, (size_t)d->num_curves * d->num_lambda, &D.curve_lut);
+  rc |= B.upload(d->cie_lut, 3 * (size_t)d->num_lambda, &D.cie_lut);
+  if (rc) return bail(rc);
+  D.tlas_root = tlas.root;
+  D.num_instances = d->num_instances;
+  D.num_lights = d->num_lights;
+  D.num_lambda = d->num_lambda;
+  D.lut_lo = d->lut_lambda_lo;
+  D.lut_hi = d->lut_lambda_hi;
+
+  std::vector<DevTexture> texs(d->num_textures);
+  size_t tex_bytes = 0;
+  for (uint32_t t = 0; t < d->num_textures; ++t) {
+    const RptTexture &T = d->textures[t];
+    size_t n = (size_t)T.width * T.height * T.channels;
+    if (B.upload(T.texels, n, &texs[t].texels)) return bail(1);
+    tex_bytes += n * sizeof(float);
+    texs[t].channels = T.channels;
+    texs[t].width = T.width;
+    texs[t].height = T.height;
+    std::memcpy(texs[t].curves, T.curves, sizeof(T.curves));
+  }
+  rc |= B.upload(texs.data(), texs.size(), &D.textures);
+  rc |= B.upload(d->texstack_textures, d->num_texstack_textures, &D.stack_tex);
+  rc |= B.upload(d->texstacks, d->num_texstacks, &D.stacks);
+  if (rc) return bail(rc);
+
+  const RptEnvironment &E = d->environment;
+  D.env_kind = E.kind;
+  D.env_strength = E.strength;
+  D.env_curve = E.curve;
+  D.env_angular_diameter = E.angular_diameter;
+  D.env_sun_dir = make_float3(E.sun_direction[0], E.sun_direction[1], E.sun_direction[2]);
+  D.env_texstack = E.texstack;
+  to3x4(E.rot_forward, D.env_rot_fwd);
+  to3x4(E.rot_reverse, D.env_rot_rev);
+  if (E.kind == RPT_ENV_HDR && E.imap_rows) {
+    size_t n = (size_t)E.imap_rows * E.imap_cols;
+    D.imap_rows = E.imap_rows;
+    D.imap_cols = E.imap_cols;
+    D.imap_marginal_n = E.imap_marginal_n;
+    D.imap_marginal_integral = E.imap_marginal_integral;
+    rc |= B.upload(E.imap_row_pdf, n, &D.imap_row_pdf);
+    rc |= B.upload(E.imap_row_cdf, n, &D.imap_row_cdf);
+    rc |= B.upload(E.imap_marginal_pdf, E.imap_marginal_n, &D.imap_m_pdf);
+    rc |= B.upload(E.imap_marginal_cdf, E.imap_marginal_n, &D.imap_m_cdf);
+    if (rc) return bail(rc);
+    tex_bytes += (2 * n + 2 * E.imap_marginal_n) * sizeof(float);
+  }
+  D.p_env = d->num_lights == 0 ? 1.0f : d->env_sampling_probability;  // world/mod.rs:77-80,170-176
+  float span[3] = {world.mx[0] - world.mn[0], world.mx[1] - world.mn[1], world.mx[2] - world.mn[2]};
+  D.world_radius = std::sqrt(span[0] * span[0] + span[1] * span[1] + span[2] * span[2]) / 2.0f;
+  S->cameras.assign(d->cameras, d->cameras + d->num_cameras);
+
+  S->stats.instances = d->num_instances;
+  S->stats.node_bytes = nodes.size() * sizeof(DevNode);
+  S->stats.triangle_bytes = tri_verts.size() * sizeof(float4) + tri_normals.size() * sizeof(float4);
+  S->stats.scene_bytes_total = S->stats.node_bytes + S->stats.triangle_bytes + insts.size() * sizeof(DevInstance) +
+                               (size_t)d->num_curves * d->num_lambda * 4 + tex_bytes;
+
+  size_t film_smem = 3 * (size_t)d->num_lambda * sizeof(float);
+  if (film_smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(k_film, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)film_smem) != cudaSuccess)
+      return bail(fail("num_lambda too large for the film kernel's shared-memory CIE tables"));
+  }
+  S->grid[K_RAYGEN] = occupancy_grid(k_raygen, 256, 0, S->num_sms);
+  S->grid[K_TRACE] = occupancy_grid(k_trace, TRACE_THREADS, 0, S->num_sms);
+  S->grid[K_SHADE_MISS] = occupancy_grid(k_shade_miss, 256, 0, S->num_sms);
+  S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_surface<Q_DIFFUSE>, 128, 0, S->num_sms);
+  S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_surface<Q_GGX>, 128, 0, S->num_sms);
+  S->grid[K_SHADOW] = occupancy_grid(k_shadow, TRACE_THREADS, 0, S->num_sms);
+  S->grid[K_FILM] = occupancy_grid(k_film, 256, film_smem, S->num_sms);
+  *out = S;
+  return 0;
+}
+
+int rpt_render_pt_device(RptScene *S, const RptRenderParams *P, void **film_dev, RptCounters *counters) {
+  if (!film_dev) return fail("null argument");
+  if (int rc = render_waves(S, P, counters)) return rc;
+  if (P->spp_total) {
+    k_scale<<<S->num_sms * 4, 256, 0, S->stream>>>(S->film, S->film_pixels, 1.0f / (float)P->spp_total);
+    CUDA_TRY(cudaStreamSynchronize(S->stream));
+  }
+  *film_dev = S->film;
+  return 0;
+}
+
+int rpt_render_pt(RptScene *S, const RptRenderParams *P, float *film_xyzw, RptCounters *counters) {
+  if (!film_xyzw) return fail("null argument");
+  void *dev = nullptr;
+  if (int rc = rpt_render_pt_device(S, P, &dev, counters)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(film_xyzw, dev, S->film_pixels * sizeof(float4), cudaMemcpyDeviceToHost, S->stream));
+  CUDA_TRY(cudaStreamSynchronize(S->stream));
+  return 0;
+}
+
+int rpt_film_scale(RptScene *S, void *film_dev, uint64_t n_float4, float scale) {
+  if (!S || !film_dev) return fail("null argument");
+  CUDA_TRY(cudaSetDevice(S->device));
+  k_scale<<<S->num_sms * 4, 256, 0, S->stream>>>(static_cast<float4 *>(film_dev), n_float4, scale);
+  CUDA_TRY(cudaStreamSynchronize(S->stream));
+  return 0;
+}
+
+int rpt_trace_primary(RptScene *S, const RptRenderParams *P, uint32_t *inst, uint32_t *prim, float *t) {
+  if (int rc = validate(S, P)) return rc;
+  if (!inst || !prim || !t) return fail("null argument");
+  CUDA_TRY(cudaSetDevice(S->device));
+  size_t wh = (size_t)P->width * P->height;
+  if (int rc = ensure_wave(S, wh, wh * P->light_samples)) return rc;
+  RenderCtx R = make_ctx(S, P);
+  R.n_slots = (uint32_t)wh;
+  R.sample_base = P->spp_offset;
+  WaveBuffers &w = S->wave;
+  CUDA_TRY(cudaMemsetAsync(w.counts, 0, (RPT_MAX_BOUNCES + 1) * Q_COUNT * sizeof(uint32_t), S->stream));
+  k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
+  k_trace<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts);
+  std::vector<HitRec> h(wh);
+  CUDA_TRY(cudaMemcpyAsync(h.data(), w.hits, wh * sizeof(HitRec), cudaMemcpyDeviceToHost, S->stream));
+  CUDA_TRY(cudaStreamSynchronize(S->stream));
+  CUDA_TRY(cudaGetLastError());
+  for (size_t i = 0; i < wh; ++i) {
+    inst[i] = h[i].inst;
+    prim[i] = h[i].prim;
+    t[i] = h[i].t;
+  }
+  return 0;
+}
+
+int rpt_trace_rays(RptScene *S, uint32_t n, const float *origins, const float *dirs, const float *tmax, uint32_t *inst, uint32_t *prim, float *t) {
+  if (!S || !origins || !dirs || !tmax || !inst || !prim || !t) return fail("null argument");
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(S->device));
+  float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+  HitRec *d_h = nullptr;
+  CUDA_TRY(cudaMalloc(&d_o, 3 * (size_t)n * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_d, 3 * (size_t)n * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_t, (size_t)n * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_h, (size_t)n * sizeof(HitRec)));
+  CUDA_TRY(cudaMemcpyAsync(d_o, origins, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_d, dirs, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_t, tmax, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
+  k_trace_rays<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
+  std::vector<HitRec> h(n);
+  CUDA_TRY(cudaMemcpyAsync(h.data(), d_h, (size_t)n * sizeof(HitRec), cudaMemcpyDeviceToHost, S->stream));
+  CUDA_TRY(cudaStreamSynchronize(S->stream));
+  cudaFree(d_o);
+  cudaFree(d_d);
+  cudaFree(d_t);
+  cudaFree(d_h);
+  CUDA_TRY(cudaGetLastError());
+  for (uint32_t i = 0; i < n; ++i) {
+    inst[i] = h[i].inst;
+    prim[i] = h[i].prim;
+    t[i] = h[i].t;
+  }
+  return 0;
+}
+
+int rpt_last_kernel_times(RptScene *S, RptKernelTime *out, uint32_t cap, uint32_t *n) {
+  if (!S || !out || !n) return fail("null argument");
+  uint32_t k = 0;
+  for (int i = 0; i < K_NUM && k < cap; ++i) {
+    if (S->kernel_launches[i] == 0) continue;
+    out[k].name = kKernelNames[i];
+    out[k].launches = S->kernel_launches[i];
+    out[k].ms = S->kernel_ms[i];
+    ++k;
+  }
+  *n = k;
+  return 0;
+}
+
+int rpt_scene_stats(RptScene *S, RptSceneStats *out) {
+  if (!S || !out) return fail("null argument");
+  *out = S->stats;
+  return 0;
+}
+
+}  // extern "C"

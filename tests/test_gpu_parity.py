@@ -1,0 +1,163 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs. BASELINE.json's three checks: (a) primary-hit ids >= 99.99 %, (b) furnace within 1e-3,
+(c) converged images within a stated relMSE tolerance in linear XYZ."""
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+ALL_SCENES = ["cornell", "furnace", "furnace_exact", "gem", "hdri", "test_nee_sphere", "orb_caustic", "sun_test",
+              "parallel_prism", "lighting_north", "rtiow2"]
+
+
+@pytest.fixture(scope="module")
+def scenes():
+    cache = {}
+
+    def get(name, w, h, spp):
+        key = (name, w, h, spp)
+        if key not in cache:
+            world, st, flat = parity.load_scene(name, w, h, spp)
+            cache[key] = (st, parity.cuda_scene(flat), parity.oracle_scene(flat))
+        return cache[key]
+
+    yield get
+    for st, cs, os_ in cache.values():
+        cs.close()
+        os_.close()
+
+
+@pytest.mark.parametrize("name", ALL_SCENES + ["instanced_monkeys"])
+def test_primary_hit_ids(scenes, name):
+    """(a) primary-ray hit (instance, primitive) ids match on >= 99.99 % of pixels."""
+    w, h = (320, 180) if name != "instanced_monkeys" else (256, 144)
+    st, cs, os_ = scenes(name, w, h, 1)
+    p = st.params(seed=3)
+    gi, gp, gt = cs.trace_primary(p)
+    oi, op, ot = os_.trace_primary(p)
+    same = (gi == oi) & (gp == op)
+    frac = float(np.mean(same))
+    assert frac >= 0.9999, f"{name}: only {frac:.6f} of primary hits match"
+    both = same & (gi != 0xFFFFFFFF)
+    if both.any():
+        assert np.allclose(gt[both], ot[both], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["cornell", "gem", "test_nee_sphere", "instanced_monkeys"])
+def test_random_rays(scenes, name):
+    """Closest hits of random rays from inside the scene bounds match the oracle (ids bit-exact)."""
+    st, cs, os_ = scenes(name, 64, 64, 1)
+    rng = np.random.default_rng(11)
+    n = 20000
+    scale = 40.0 if name == "instanced_monkeys" else 1.0
+    o = (rng.uniform(-0.9, 0.9, size=(n, 3)) * scale).astype(np.float32)
+    if name == "cornell":
+        o = (rng.uniform(0.01, 0.54, size=(n, 3))).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    tmax = np.full(n, np.inf, dtype=np.float32)
+    gi, gp, gt = cs.trace_rays(o, d, tmax)
+    oi, op, ot = os_.trace_rays(o, d, tmax)
+    frac = float(np.mean((gi == oi) & (gp == op)))
+    assert frac >= 0.9999, f"{name}: {frac:.6f}"
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
+def test_same_stream_images(scenes, name):
+    """Same Philox streams on both sides: the low-spp images agree far below the noise floor.
+    Tolerance: relMSE(XYZ) <= 2e-3 and mean-Y within 2e-3 (divergence only where fp32 rounding flips a
+    branch: a russian-roulette decision, a grazing hit)."""
+    st, cs, os_ = scenes(name, 96, 54, 8)
+    p = st.params(seed=5)
+    fg, cg = cs.render_pt(p)
+    fo, co = os_.render_pt(p)
+    assert np.isfinite(fg).all()
+    assert parity.mean_rel_diff(fg, fo) < 2e-3, (name, fg[..., 1].mean(), fo[..., 1].mean())
+    assert parity.rel_mse(fg, fo) < 2e-3, (name, parity.rel_mse(fg, fo))
+    # Profile counters (profile.rs): identical up to the rare divergent paths
+    for k in ("camera_rays",):
+        assert getattr(cg, k) == getattr(co, k)
+    for k in ("bounce_rays", "shadow_rays", "env_hits", "segments"):
+        a, b = getattr(cg, k), getattr(co, k)
+        assert abs(a - b) <= max(4, 2e-3 * b), (name, k, a, b)
+
+
+def test_furnace_exact(scenes):
+    """(b) white furnace: Constant env 1.0, unit Lambertian sphere with albedo clamped to 1, p_env = 1.
+    Pixels covered by the sphere and background pixels both return 1.0 within 1e-3 ... of the oracle; the
+    absolute value is reported next to 1.0 (the reference's uniform-uv env sampling with a
+    1/4pi pdf biases NEE, MIS only partly hides it)."""
+    st, cs, os_ = scenes("furnace_exact", 128, 128, 256)
+    p = st.params(seed=9)
+    fg, _ = cs.render_pt(p)
+    fo, _ = os_.render_pt(p)
+    yg, yo = float(fg[..., 1].mean()), float(fo[..., 1].mean())
+    assert abs(yg - yo) / yo < 1e-3, (yg, yo)
+    # background pixels see the env directly: exactly the CIE-weighted mean of a unit spectrum
+    corner_g, corner_o = float(fg[:8, :8, 1].mean()), float(fo[:8, :8, 1].mean())
+    assert abs(corner_g - corner_o) / corner_o < 1e-3
+    centre_g = float(fg[56:72, 56:72, 1].mean())
+    print(f"furnace_exact: mean Y gpu {yg:.6f} oracle {yo:.6f}; centre/corner = {centre_g / corner_g:.4f} (1.0 = energy conserving)")
+
+
+def test_furnace_shipped(scenes):
+    """(b) the shipped white_furnace scene (rough glass sphere, camera inside): GPU == oracle within 1e-3 on mean Y."""
+    st, cs, os_ = scenes("furnace", 96, 96, 128)
+    p = st.params(seed=2)
+    fg, _ = cs.render_pt(p)
+    fo, _ = os_.render_pt(p)
+    assert parity.mean_rel_diff(fg, fo) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["cornell", "test_nee_sphere", "orb_caustic"])
+def test_converged_images_independent_seeds(scenes, name):
+    """(c) converged images from INDEPENDENT seeds: relMSE(GPU seed A, oracle seed B) must sit at the
+    oracle's own two-seed noise floor relMSE(oracle seed B, oracle seed C) (within 1.5x)."""
+    st, cs, os_ = scenes(name, 64, 36, 512)
+    fg, _ = cs.render_pt(st.params(seed=101))
+    fo1, _ = os_.render_pt(st.params(seed=202))
+    fo2, _ = os_.render_pt(st.params(seed=303))
+    floor = parity.rel_mse(fo2, fo1)
+    got = parity.rel_mse(fg, fo1)
+    assert got < 1.5 * floor + 1e-5, (name, got, floor)
+    assert parity.mean_rel_diff(fg, fo1) < 3 * parity.mean_rel_diff(fo2, fo1) + 5e-3
+
+
+def test_spp_split_equals_whole(scenes):
+    """Multi-GPU partition property: rendering spp as two offset halves and summing equals the whole."""
+    st, cs, _ = scenes("cornell", 96, 54, 8)
+    whole, _ = cs.render_pt(st.params(seed=4, spp=8, spp_offset=0, spp_total=8))
+    a, _ = cs.render_pt(st.params(seed=4, spp=4, spp_offset=0, spp_total=8))
+    b, _ = cs.render_pt(st.params(seed=4, spp=4, spp_offset=4, spp_total=8))
+    assert np.allclose(a + b, whole, rtol=1e-4, atol=1e-7)
+
+
+def test_empty_and_edge_cases(scenes, pkg):
+    st, cs, _ = scenes("cornell", 96, 54, 8)
+    film, cnt = cs.render_pt(st.params(seed=1, spp=0))
+    assert not film.any() and cnt.camera_rays == 0
+    with pytest.raises(pkg.ffi.RptError):
+        p = st.params(seed=1)
+        p.camera = 7
+        cs.render_pt(p)
+    # ragged: 1x1 film, 1 spp; odd sizes that do not fill a warp
+    for (w, h) in ((1, 1), (33, 7)):
+        world, st2, flat = parity.load_scene("cornell", w, h, 3)
+        c2, o2 = parity.cuda_scene(flat), parity.oracle_scene(flat)
+        fg, _ = c2.render_pt(st2.params(seed=8))
+        fo, _ = o2.render_pt(st2.params(seed=8))
+        assert fg.shape == (h, w, 4) and np.isfinite(fg).all()
+        assert np.allclose(fg, fo, rtol=2e-2, atol=1e-4) or parity.rel_mse(fg, fo) < 5e-2
+        c2.close()
+        o2.close()
+
+
+def test_kernel_times_and_stats(scenes):
+    st, cs, _ = scenes("cornell", 96, 54, 8)
+    cs.render_pt(st.params(seed=1))
+    names = [k["name"] for k in cs.kernel_times()]
+    assert "k_trace" in names and "k_shadow" in names and "k_film" in names
+    s = cs.stats()
+    assert s["triangles"] == 30 and s["instances"] == 4

@@ -1,0 +1,204 @@
+#!/usr/bin/env python3
+"""Bakes portable scene blobs (scenes/*.npz) from the reference's own TOML / CSV / OBJ files plus the
+synthesised fixtures, so that the GPU box — which has no /root/reference — renders the same scenes.
+
+Run here (the container with /root/reference): `python tools/bake_scenes.py`.
+Each blob = flattened World + the PT settings of its config (rust-pathtracer_b200/blob.py).
+
+BASELINE.json configs:
+  C1 cornell        data/config_test_cornell_box.toml (camera_id fixed to "main")
+  C2 furnace        data/config_test_whitefurnace.toml; furnace_exact = the exact-1.0 variant (SURVEY A9 ii)
+  C3 gem            data/scenes/cornell_box_diamond_gem.toml (synthetic low-res HDR, p_env = 0)
+  C4 hdri           data/scenes/hdri_test.toml with a synthetic HDR + baked importance map
+  C5 instanced      2388 instances of data/meshes/monkey.obj (10.0 M triangles), generated scene
+plus in-tree scenes that cover every material / light / environment kind.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g  # noqa: E402
+
+pkg = g.load_package()
+from rust_pathtracer_b200 import blob, loader  # noqa: E402
+from rust_pathtracer_b200.renderer import PTSettings  # noqa: E402
+
+OUT = os.path.join(ROOT, "scenes")
+GEN = os.path.join(ROOT, "fixtures", "data", "scenes")
+
+
+def make_config(scene_file, width, height, spp, min_bounces, max_bounces, light_samples, only_direct=False, wavelength_bounds=None):
+    rs = loader.RenderSettings(
+        filename="beauty", width=width, height=height, integrator_type="PT", light_samples=light_samples, medium_aware=False,
+        min_bounces=min_bounces, max_bounces=max_bounces, hwss=False, threads=None, min_samples=spp, camera_id="main",
+        russian_roulette=True, only_direct=only_direct, wavelength_bounds=wavelength_bounds, premultiply=None)
+    return loader.Config(scene_file=scene_file, renderer={"type": "Naive"}, render_settings=[rs])
+
+
+def from_reference_config(path, **overrides):
+    cfg = loader.get_config(path)
+    for rs in cfg.render_settings:
+        rs.camera_id = "main"  # the shipped configs name cameras no scene defines
+        for k, v in overrides.items():
+            setattr(rs, k, v)
+    return cfg
+
+
+def write_generated_scenes():
+    os.makedirs(GEN, exist_ok=True)
+    libs = 'curves = "data/lib_curves.toml"\ntextures = "data/lib_textures.toml"\nmaterials = "data/lib_materials.toml"\nmeshes = "data/lib_meshes.toml"\n'
+    # exact furnace (SURVEY A9 ii): Constant flat_one env, unit Lambertian sphere with albedo clamped to 1
+    with open(os.path.join(GEN, "furnace_exact.toml"), "w") as f:
+        f.write('curves = "data/lib_curves.toml"\nmeshes = "data/lib_meshes.toml"\n' + """
+env_sampling_probability = 1.0
+[environment]
+type = "Constant"
+strength = 1.0
+color = "flat_one"
+
+[materials.lambertian_unit]
+type = "Lambertian"
+texture_id = "unit_albedo"
+
+[[textures.unit_albedo]]
+type = "Texture1"
+filename = "data/textures/single_pixel.png"
+curve = { type = "Flat", strength = 2.0 }
+
+[[instances]]
+material_name = "lambertian_unit"
+[instances.aggregate]
+type = "Sphere"
+radius = 1.0
+origin = [0.0, 0.0, 0.0]
+
+[[cameras]]
+type = "SimpleCamera"
+name = "main"
+look_from = [-5.0, 0.0, 0.0]
+look_at = [0.0, 0.0, 0.0]
+aperture_diameter = 0.001
+aperture = { type = "Circular" }
+focal_distance = 5.0
+vfov = 30.0
+""")
+    # instanced monkeys (C5): 48 x 50 grid (minus 12) = 2388 instances, Philox-free numpy RNG seed 5
+    rng = np.random.default_rng(5)
+    mats = ["lambertian_white", "ggx_gold", "ggx_copper", "ggx_glass"]
+    lines = [libs.replace('meshes = "data/lib_meshes.toml"\n', ""), """
+env_sampling_probability = 0.5
+[environment]
+type = "Sun"
+strength = 30.0
+angular_diameter = 0.05
+sun_direction = [0.3, 0.2, 1.0]
+color = "blackbody_5000k"
+
+[meshes.monkey]
+filename = "data/meshes/monkey.obj"
+
+[[instances]]
+material_name = "lambertian_white"
+[instances.aggregate]
+type = "Rect"
+size = [140.0, 140.0]
+origin = [0.0, 0.0, -1.2]
+normal = "Z"
+two_sided = true
+
+[[instances]]
+material_name = "diffuse_light"
+[instances.aggregate]
+type = "Rect"
+size = [40.0, 40.0]
+origin = [0.0, 0.0, 40.0]
+normal = "Z"
+two_sided = true
+"""]
+    count = 0
+    for gy in range(50):
+        for gx in range(48):
+            if count >= 2388:
+                break
+            axis = rng.normal(size=3)
+            axis /= np.linalg.norm(axis)
+            ang = float(rng.uniform(0, 360))
+            sc = float(rng.uniform(0.8, 1.2))
+            lines.append(f"""
+[[instances]]
+material_name = "{mats[count % 4]}"
+[instances.transform]
+scale = [{sc:.5f}, {sc:.5f}, {sc:.5f}]
+rotate = [{{ axis = [{axis[0]:.5f}, {axis[1]:.5f}, {axis[2]:.5f}], angle = {ang:.3f} }}]
+translate = [{(gx - 23.5) * 2.8:.4f}, {(gy - 24.5) * 2.8:.4f}, 0.0]
+[instances.aggregate]
+type = "Mesh"
+name = "monkey"
+""")
+            count += 1
+    lines.append("""
+[[cameras]]
+type = "SimpleCamera"
+name = "main"
+look_from = [-95.0, -60.0, 45.0]
+look_at = [0.0, 0.0, 0.0]
+aperture_diameter = 0.001
+aperture = { type = "Circular" }
+focal_distance = 100.0
+vfov = 50.0
+""")
+    with open(os.path.join(GEN, "instanced_monkeys.toml"), "w") as f:
+        f.write("".join(lines))
+
+
+def bake(name, cfg, scene_file=None, num_lambda=1024):
+    world = loader.construct_world(cfg, scene_file)
+    rs = cfg.render_settings[0]
+    st = PTSettings.from_render_settings(rs, cfg.camera_names_to_index[rs.camera_id])
+    path = os.path.join(OUT, name + ".npz")
+    blob.save_world(path, world, st.to_dict(), st.wavelength_bounds[0], st.wavelength_bounds[1], num_lambda)
+    tris = sum(len(world.meshes[i.mesh].indices) for i in world.instances if i.mesh >= 0)
+    print(f"{name:28s} {os.path.getsize(path) / 1024:9.1f} KiB  instances={len(world.instances)} tris(instanced)={tris} lights={len(world.lights)}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", nargs="*", default=None)
+    args = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    write_generated_scenes()
+    # the synthetic HDRs must exist before the HDRI scenes are parsed (small ones for the blobs)
+    import subprocess
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_fixtures.py"), "--hdri", "--hdri-width", "1024"])
+
+    jobs = {
+        # BASELINE configs[0]: Cornell, PT, 1080p @ 16 spp (the config file says 1080x1080 @ 128)
+        "cornell": lambda: bake("cornell", from_reference_config("data/config_test_cornell_box.toml", width=1920, height=1080, min_samples=16)),
+        "furnace": lambda: bake("furnace", from_reference_config("data/config_test_whitefurnace.toml")),
+        "furnace_exact": lambda: bake("furnace_exact", make_config("data/scenes/furnace_exact.toml", 256, 256, 64, 1, 8, 4)),
+        "gem": lambda: bake("gem", make_config("data/scenes/cornell_box_diamond_gem.toml", 1920, 1080, 1024, 4, 16, 2)),
+        "hdri": lambda: bake("hdri", from_reference_config("data/config_test_lighting_hdri.toml", width=3840, height=2160)),
+        "instanced_monkeys": lambda: bake("instanced_monkeys", make_config("data/scenes/instanced_monkeys.toml", 3840, 2160, 16, 2, 6, 2)),
+        # in-tree scenes covering the remaining materials / lights / environments
+        "test_nee_sphere": lambda: bake("test_nee_sphere", make_config("data/scenes/test_nee_sphere.toml", 512, 512, 32, 2, 8, 2)),
+        "orb_caustic": lambda: bake("orb_caustic", make_config("data/scenes/cornell_box_single_orb_caustic.toml", 512, 512, 32, 2, 10, 2)),
+        "sun_test": lambda: bake("sun_test", make_config("data/scenes/sun_test.toml", 512, 512, 32, 2, 8, 2)),
+        "parallel_prism": lambda: bake("parallel_prism", make_config("data/scenes/cornell_box_parallel_prism.toml", 512, 512, 32, 2, 10, 2)),
+        "lighting_north": lambda: bake("lighting_north", from_reference_config("data/config_test_lighting_north.toml")),
+        "rtiow2": lambda: bake("rtiow2", make_config("data/scenes/test_rtiow_scene_2.toml", 512, 512, 32, 2, 8, 2)),
+    }
+    for name, job in jobs.items():
+        if args.only and name not in args.only:
+            continue
+        try:
+            job()
+        except Exception as e:  # keep going: some in-tree scenes reference assets that are not shipped
+            print(f"{name:28s} SKIPPED: {type(e).__name__}: {e}")
+
+
+if __name__ == "__main__":
+    main()
