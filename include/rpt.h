@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RPT_ABI_VERSION 3u
+#define RPT_ABI_VERSION 4u
 
 /* ---- MaterialId (reference src/materials/mod.rs:22-27) --------------------------
  * Packed as (tag << 16) | table_index; RPT_MAT_NONE = "no override / no id". */
@@ -205,6 +205,12 @@ typedef struct RptCounters {
   uint64_t segments;     /* walk rays traced (one iteration of integrator/utils.rs:170) */
   uint64_t true_rays;    /* closest-hit queries issued: walk + NEE */
   uint64_t kernel_launches; /* CUDA kernels launched by this call */
+  /* BVH work of the two traversal kernels, for the roofline accounting:
+   * bytes fetched = nodes * 64 + triangles * 48 + instances * 144 */
+  uint64_t shadow_rays_traced; /* NEE rays actually traced (zero-weight ones are skipped) */
+  uint64_t walk_nodes, walk_tris, walk_insts;
+  uint64_t shadow_nodes, shadow_tris, shadow_insts;
+  double device_ms; /* device time of the call: first to last CUDA event on the library's stream */
 } RptCounters;
 
 typedef struct RptScene RptScene; /* opaque */

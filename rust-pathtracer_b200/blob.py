@@ -26,6 +26,8 @@ class LutCurve(C.Curve):
         lam = np.asarray(lam, dtype=F32)
         n = len(self.values)
         x = np.clip((lam - F32(self.lo)) / F32(self.hi - self.lo) * F32(n - 1), 0, n - 1)
+        snapped = np.round(x)
+        x = np.where(np.abs(x - snapped) < 1e-3, snapped, x).astype(F32)  # re-sampling on the stored grid is exact
         i = np.minimum(x.astype(np.int64), n - 2)
         t = (x - i.astype(F32)).astype(F32)
         a, b = self.values[i], self.values[i + 1]

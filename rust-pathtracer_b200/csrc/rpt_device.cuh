@@ -417,8 +417,14 @@ __device__ __forceinline__ uint64_t tie_key(bool strict, uint32_t inst_order, ui
 // instance.rs:75-133, mesh.rs:314-360). Unlike the reference (F8) it prunes by the closest hit so far;
 // results are identical because pruned boxes cannot contain a closer hit.
 // `stack` is this thread's slice of the CTA's shared-memory traversal stack, strided by `stride`.
+// Work counters for the roofline accounting (bytes fetched per ray = nodes * 64 B + triangles * 48 B + instances * 144 B).
+struct TraceWork {
+  uint32_t nodes, tris, insts;
+};
+
 template <bool ANY_HIT>
-__device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d, float tmax, int *stack, int stride, TraceHit &out) {
+__device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d, float tmax, int *stack, int stride, TraceHit &out,
+                                          TraceWork &work) {
   float closest = tmax;
   uint64_t best_key = 0;
   bool found = false;
@@ -436,6 +442,7 @@ __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d,
 
   while (true) {
     if (cur >= 0 && cur != RPT_SENTINEL) {
+      work.nodes++;
       const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
       float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
       int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
@@ -467,6 +474,7 @@ __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d,
       uint32_t idx = (uint32_t)(~cur);
       if (cur_inst == RPT_NONE) {
         // TLAS leaf: an instance
+        work.insts++;
         const DevInstance &I = S.instances[idx];
         uint32_t flags = I.flags;
         float3 lo = o, ld = d;
@@ -512,6 +520,7 @@ __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d,
         }
       } else {
         // BLAS leaf: a triangle of the current mesh instance
+        work.tris++;
         uint32_t tri = cur_tri_base + idx;
         const float4 *tv = S.tri_verts + 3 * (size_t)tri;
         float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);

@@ -83,6 +83,7 @@ struct WaveBuffers {
   uint32_t *sh_c;       // slot | kind << 31 (1 = environment any-hit)
   float *acc;           // per-slot energy (pt.rs `sum.energy`)
   uint32_t *counts;     // [RPT_MAX_BOUNCES + 1][Q_COUNT]
+  unsigned long long *work;  // [2][3]: (nodes, triangles, instances) visited by k_trace / k_shadow
 };
 
 __device__ __forceinline__ float3 rec_origin(const PathRec &r) {
@@ -119,6 +120,22 @@ __device__ __forceinline__ uint32_t warp_append_n(uint32_t *counter, uint32_t n)
 }
 
 #define TRACE_THREADS 128
+
+// per-thread BVH work counters -> one 64-bit atomic per warp per counter at kernel end
+__device__ __forceinline__ void flush_work(const TraceWork &w, unsigned long long *work) {
+  uint32_t a = w.nodes, b = w.tris, c = w.insts;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+    b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  }
+  if ((threadIdx.x & 31u) == 0) {
+    atomicAdd(work + 0, (unsigned long long)a);
+    atomicAdd(work + 1, (unsigned long long)b);
+    atomicAdd(work + 2, (unsigned long long)c);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -160,8 +177,10 @@ __device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t m
 // Closest-hit traversal of the path queue; appends each path to the list of its vertex's class.
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
                                                          uint32_t *__restrict__ q_miss, uint32_t *__restrict__ q_diffuse,
-                                                         uint32_t *__restrict__ q_ggx, uint32_t *__restrict__ counts) {
+                                                         uint32_t *__restrict__ q_ggx, uint32_t *__restrict__ counts,
+                                                         unsigned long long *__restrict__ work) {
   __shared__ int s_stack[RPT_STACK_SIZE * TRACE_THREADS];
+  TraceWork tw{0, 0, 0};
   const uint32_t n = counts[Q_PATHS];
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t n_round = (n + 31u) & ~31u;  // keep whole warps in the loop for the ballots
@@ -177,7 +196,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, const PathR
       r.r3 = __ldg(rp + 3);
       float3 o = rec_origin(r), d = f3(r.r2);
       TraceHit th;
-      bool hit = trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th);
+      bool hit = trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
       HitRec h;
       h.t = th.t;
       h.inst = th.inst;
@@ -204,6 +223,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, const PathR
     k = warp_append(counts + Q_GGX, cls == Q_GGX);
     if (cls == Q_GGX) q_ggx[k] = i;
   }
+  flush_work(tw, work);
 }
 
 // Environment vertex (integrator/utils.rs:344-373 + pt.rs:487-511).
@@ -434,8 +454,9 @@ __global__ void __launch_bounds__(128) k_shade_surface(DevScene S, RenderCtx R, 
 // emission is used (pt.rs:177-218, F9). Environment samples: any hit kills the sample (pt.rs:254-263).
 __global__ void __launch_bounds__(TRACE_THREADS) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
                                                           const uint32_t *__restrict__ sh_c, const uint32_t *__restrict__ counts,
-                                                          float *__restrict__ acc) {
+                                                          float *__restrict__ acc, unsigned long long *__restrict__ work) {
   __shared__ int s_stack[RPT_STACK_SIZE * TRACE_THREADS];
+  TraceWork tw{0, 0, 0};
   const uint32_t n = counts[Q_SHADOW];
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -446,9 +467,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_shadow(DevScene S, const floa
     uint32_t slot = c & 0x7FFFFFFFu;
     TraceHit th;
     if (c & 0x80000000u) {
-      if (!trace_ray<true>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th)) atomicAdd(acc + slot, pre);
+      if (!trace_ray<true>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) atomicAdd(acc + slot, pre);
     } else {
-      if (trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th)) {
+      if (trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) {
         SurfaceHit sh;
         reconstruct_hit(S, o, d, th, sh);
         if (RPT_MAT_IS_LIGHT(sh.material)) {
@@ -464,6 +485,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_shadow(DevScene S, const floa
       }
     }
   }
+  flush_work(tw, work);
 }
 
 // XYZColor::from(SingleWavelength) (pt.rs:614) + per-pixel accumulation (tiled.rs:390).
@@ -519,8 +541,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32
   uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     TraceHit th;
+    TraceWork tw{0, 0, 0};
     trace_ray<false>(S, f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), tmax[i], s_stack + threadIdx.x,
-                     TRACE_THREADS, th);
+                     TRACE_THREADS, th, tw);
     HitRec h;
     h.t = th.t;
     h.inst = th.inst;
@@ -638,7 +661,7 @@ int occupancy_grid(K kernel, int threads, size_t smem, int num_sms) {
 
 int free_wave(RptScene *S) {
   WaveBuffers &w = S->wave;
-  void *ptrs[] = {w.paths[0], w.paths[1], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.sh_a, w.sh_b, w.sh_c, w.acc, w.counts};
+  void *ptrs[] = {w.paths[0], w.paths[1], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.sh_a, w.sh_b, w.sh_c, w.acc, w.counts, w.work};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   w = WaveBuffers{};
@@ -661,6 +684,8 @@ int ensure_wave(RptScene *S, size_t slots, size_t shadow) {
   CUDA_TRY(cudaMalloc(&w.sh_c, std::max<size_t>(shadow, 1) * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&w.acc, slots * sizeof(float)));
   CUDA_TRY(cudaMalloc(&w.counts, (RPT_MAX_BOUNCES + 1) * Q_COUNT * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.work, 6 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(w.work, 0, 6 * sizeof(unsigned long long)));
   S->wave_slots = slots;
   S->wave_shadow = shadow;
   return 0;
@@ -756,6 +781,9 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   RptCounters C{};
   size_t film_smem = 3 * (size_t)S->dev.num_lambda * sizeof(float);
 
+  CUDA_TRY(cudaMemsetAsync(w.work, 0, 6 * sizeof(unsigned long long), S->stream));
+  size_t ev_first = S->ev_used;
+  cudaEventRecord(T.next_event(), S->stream);
   for (uint32_t done = 0; done < P->spp; done += spp_chunk) {
     uint32_t chunk = std::min(spp_chunk, P->spp - done);
     R.n_slots = (uint32_t)(wh * chunk);
@@ -769,7 +797,7 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       uint32_t *cb = w.counts + (size_t)b * Q_COUNT, *cn = w.counts + (size_t)(b + 1) * Q_COUNT;
       PathRec *in = w.paths[b & 1], *out = w.paths[(b + 1) & 1];
       T.begin(K_TRACE);
-      k_trace<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb);
+      k_trace<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work);
       T.end();
       T.begin(K_SHADE_MISS);
       k_shade_miss<<<S->grid[K_SHADE_MISS], 256, 0, S->stream>>>(S->dev, in, w.q_miss, cb, w.acc);
@@ -782,7 +810,7 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       T.end();
       if (P->light_samples > 0) {
         T.begin(K_SHADOW);
-        k_shadow<<<S->grid[K_SHADOW], TRACE_THREADS, 0, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc);
+        k_shadow<<<S->grid[K_SHADOW], TRACE_THREADS, 0, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc, w.work + 3);
         T.end();
       }
     }
@@ -802,7 +830,24 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       C.env_hits += c[Q_MISS];
       C.bounce_rays += c[Q_MISS] + c[Q_DIFFUSE] + c[Q_GGX] - c[Q_NAN];
       C.shadow_rays += c[Q_SHADOW_REF];
+      C.shadow_rays_traced += c[Q_SHADOW];
     }
+  }
+  size_t ev_last = S->ev_used;
+  cudaEventRecord(T.next_event(), S->stream);
+  unsigned long long h_work[6];
+  CUDA_TRY(cudaMemcpyAsync(h_work, w.work, sizeof(h_work), cudaMemcpyDeviceToHost, S->stream));
+  CUDA_TRY(cudaStreamSynchronize(S->stream));
+  C.walk_nodes = h_work[0];
+  C.walk_tris = h_work[1];
+  C.walk_insts = h_work[2];
+  C.shadow_nodes = h_work[3];
+  C.shadow_tris = h_work[4];
+  C.shadow_insts = h_work[5];
+  {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, S->ev_pool[ev_first], S->ev_pool[ev_last]);
+    C.device_ms = ms;
   }
   for (auto &sp : S->spans) {
     float ms = 0.0f;
@@ -1128,7 +1173,7 @@ int rpt_trace_primary(RptScene *S, const RptRenderParams *P, uint32_t *inst, uin
   WaveBuffers &w = S->wave;
   CUDA_TRY(cudaMemsetAsync(w.counts, 0, (RPT_MAX_BOUNCES + 1) * Q_COUNT * sizeof(uint32_t), S->stream));
   k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
-  k_trace<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts);
+  k_trace<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts, w.work);
   std::vector<HitRec> h(wh);
   CUDA_TRY(cudaMemcpyAsync(h.data(), w.hits, wh * sizeof(HitRec), cudaMemcpyDeviceToHost, S->stream));
   CUDA_TRY(cudaStreamSynchronize(S->stream));

@@ -17,7 +17,7 @@ from . import curves as C
 from . import world as W
 
 F32 = np.float32
-ABI_VERSION = 3
+ABI_VERSION = 4
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "librpt_b200.so")
@@ -105,10 +105,12 @@ class RptCounters(ct.Structure):
     _fields_ = [
         ("camera_rays", c_u64), ("bounce_rays", c_u64), ("shadow_rays", c_u64), ("light_rays", c_u64),
         ("env_hits", c_u64), ("segments", c_u64), ("true_rays", c_u64), ("kernel_launches", c_u64),
+        ("shadow_rays_traced", c_u64), ("walk_nodes", c_u64), ("walk_tris", c_u64), ("walk_insts", c_u64),
+        ("shadow_nodes", c_u64), ("shadow_tris", c_u64), ("shadow_insts", c_u64), ("device_ms", ct.c_double),
     ]
 
     def as_dict(self) -> dict:
-        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+        return {k: (float(getattr(self, k)) if k == "device_ms" else int(getattr(self, k))) for k, _ in self._fields_}
 
 
 class RptKernelTime(ct.Structure):

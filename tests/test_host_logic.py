@@ -1,0 +1,175 @@
+"""Host-side logic: loader (the mirror of the reference's parsers), curves, blobs, spp split, and the N > 1
+reduce path on CPU with gloo (world_size 2)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE_REF = os.path.isdir("/root/reference/data")
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="reference data tree not present (GPU box)")
+
+
+def test_split_spp_partitions_exactly(pkg):
+    for total in (1, 7, 16, 1024, 1000):
+        for ws in (1, 2, 3, 4, 8):
+            parts = [pkg.split_spp(total, ws, r) for r in range(ws)]
+            assert sum(c for c, _ in parts) == total
+            off = 0
+            for c, o in parts:
+                assert o == off
+                off += c
+            assert max(c for c, _ in parts) - min(c for c, _ in parts) <= 1
+
+
+def test_curve_evaluators(pkg):
+    C = pkg.curves
+    lam = np.array([400.0, 500.0, 600.0], dtype=np.float32)
+    assert np.allclose(C.Cauchy(1.4, 4500.0).evaluate(lam), 1.4 + 4500.0 / lam ** 2)
+    flat = C.cie_e(0.78)
+    assert np.allclose(flat.evaluate(lam), 0.78) and flat.evaluate(np.array([100.0], dtype=np.float32))[0] == 0.0
+    tab = C.Tabulated(np.array([400.0, 500.0, 600.0]), np.array([0.0, 8.0, 15.6]), "Linear")
+    assert np.allclose(tab.evaluate(np.array([450.0, 350.0, 700.0], dtype=np.float32)), [4.0, 0.0, 15.6])
+    cub = C.Tabulated(np.array([400.0, 500.0]), np.array([1.0, 3.0]), "Cubic")
+    assert np.isclose(cub.evaluate(np.array([450.0], dtype=np.float32))[0], 2.0)  # smoothstep midpoint
+    spike = C.Exponential([(500.0, 100.0, 100.0, 0.55)])
+    assert np.isclose(spike.evaluate(np.array([500.0], dtype=np.float32))[0], 0.55)
+    bb = C.Blackbody(5000.0, 1.0)
+    peak = 2.8977721e-3 / 5000.0 * 1e9
+    assert np.isclose(bb.evaluate(np.array([peak], dtype=np.float32))[0], 1.0, rtol=1e-3)
+    # y_bar peaks near 555-570 nm with value ~1
+    xyz = C.cie_xyz_bar(np.array([560.0], dtype=np.float32))
+    assert 0.95 < xyz[1, 0] < 1.05
+    cdf = C.Linear(np.array([1.0, 3.0], dtype=np.float32), (0.0, 1.0), "Nearest").to_cdf((0.0, 1.0), 100)
+    assert np.allclose(cdf.cdf_signal, [0.25, 1.0]) and np.isclose(cdf.pdf_integral, 2.0)
+
+
+@needs_ref
+def test_parse_reference_fixtures(pkg):
+    """test_parse_cornell / test_parse_tabulated_curve / test_parse_linear_spectra (parsing/curves.rs:410-477)."""
+    C = pkg.curves
+    ident = lambda x: np.float32(x)
+    text = open("/root/reference/data/test/cornell.csv").read()
+    white = C.parse_tabulated_csv(text, 1, "Cubic", ident, ident)
+    assert len(white.xs) > 10 and np.all(np.diff(white.xs) > 0) and 0 <= white.ys.min() and white.ys.max() <= 1.0
+    gold = C.parse_tabulated_csv(open("/root/reference/data/test/gold.csv").read(), 2, "Cubic", lambda x: np.float32(x) * 1000, ident)
+    assert gold.evaluate(np.array([550.0], dtype=np.float32))[0] > 1.0  # kappa of gold in the green
+    xe = C.parse_linear(open("/root/reference/data/test/xenon_lamp.spectra").read(), "Cubic", ident, ident)
+    assert xe.bounds[1] > xe.bounds[0] and len(xe.signal) > 10
+
+
+@needs_ref
+def test_parsing_config(pkg):
+    """test_parsing_config (parsing/mod.rs:672-686): every render setting has a filename and threads > 0."""
+    cfg = pkg.loader.get_config("data/config.toml")
+    assert cfg.render_settings
+    for rs in cfg.render_settings:
+        assert rs.filename is not None and rs.threads > 0
+
+
+@needs_ref
+def test_shipped_configs_name_undefined_cameras(pkg):
+    """data/config_test_*.toml name cameras no scene defines; the loader reports what the reference panics on."""
+    cfg = pkg.loader.get_config("data/config_test_cornell_box.toml")
+    with pytest.raises(pkg.loader.LoadError, match="cameras.rs:196"):
+        pkg.loader.construct_world(cfg)
+
+
+@needs_ref
+def test_construct_world_cornell(pkg):
+    cfg = pkg.loader.get_config("data/config_test_cornell_box.toml")
+    for rs in cfg.render_settings:
+        rs.camera_id = "main"
+    w = pkg.loader.construct_world(cfg)
+    assert len(w.instances) == 4 and len(w.lights) == 1 and w.lights[0] == 0
+    assert w.materials[0].name == "error" and w.materials[0].is_light  # mauve error light at index 0
+    assert sum(len(m.indices) for m in w.meshes) == 30
+    assert w.env_sampling_probability == 0.0
+    st = pkg.PTSettings.from_render_settings(cfg.render_settings[0], 0)
+    assert (st.min_bounces, st.max_bounces, st.light_samples) == (1, 12, 2)
+    assert st.wavelength_bounds == (380.0, 750.0)
+
+
+@needs_ref
+def test_world_intersection(pkg, oracle):
+    """test_world_intersection (world/mod.rs:266-292): a ray from (0,0,7) toward -Z hits something in test_lighting_north."""
+    import parity
+    from tools_helpers import world_from_scene
+
+    world, st = world_from_scene(pkg, "data/scenes/test_lighting_north.toml")
+    flat = pkg.ffi.FlatScene(world, *st.wavelength_bounds)
+    sc = pkg.ffi.Scene(oracle, flat, 0, "rpto")
+    inst, prim, t = sc.trace_rays(np.array([[0, 0, 7]], dtype=np.float32), np.array([[0, 0, -1]], dtype=np.float32), np.array([np.inf], dtype=np.float32))
+    assert inst[0] != 0xFFFFFFFF and np.isfinite(t[0])
+    sc.close()
+
+
+def test_obj_loader_triangulates_and_splits(pkg, tmp_path):
+    d = tmp_path / "data" / "meshes"
+    d.mkdir(parents=True)
+    (d / "q.mtl").write_text("newmtl a\nnewmtl b\n")
+    (d / "q.obj").write_text("mtllib q.mtl\no first\nusemtl a\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\nusemtl b\nv 0 0 1\nf 1 2 5\n")
+    models, mtl = pkg.loader.load_obj_models(pkg.loader.Resolver([str(tmp_path)]), "data/meshes/q.obj")
+    assert mtl == ["a", "b"] and len(models) == 2
+    assert len(models[0].indices) == 2 and len(models[1].indices) == 1  # quad -> fan of 2; usemtl change -> new model
+    assert int(models[1].face_material[0]) & 0xFFFF == 1
+
+
+def test_blob_roundtrip(pkg, tmp_path):
+    import parity
+
+    world, st, flat = parity.load_scene("gem", 32, 18, 2)
+    path = str(tmp_path / "gem.npz")
+    pkg.blob.save_world(path, world, st.to_dict(), *st.wavelength_bounds, 1024)
+    w2, s2, lut = pkg.blob.load_world(path)
+    f2 = pkg.ffi.FlatScene(w2, st.wavelength_bounds[0], st.wavelength_bounds[1], 1024)
+    assert np.allclose(f2.curve_lut, flat.curve_lut, rtol=1e-6, atol=1e-7)
+    assert len(w2.instances) == len(world.instances) and s2["width"] == 32
+    assert np.array_equal(w2.meshes[0].indices, world.meshes[0].indices)
+
+
+def test_importance_map_tables(pkg):
+    import parity
+
+    world, st, flat = parity.load_scene("hdri", 32, 18, 1)
+    e = world.environment
+    assert e.imap_row_pdf is not None
+    assert np.allclose(e.imap_row_pdf.sum(axis=1), 1.0, atol=1e-3)
+    assert np.allclose(e.imap_row_cdf[:, -1], 1.0, atol=1e-4) and np.all(np.diff(e.imap_row_cdf, axis=1) >= -1e-7)
+    assert np.isclose(e.imap_marginal_cdf[-1], 1.0, atol=1e-5)
+    assert np.isclose(e.imap_marginal_integral, 1.0 / len(e.imap_marginal_pdf), rtol=1e-3)
+
+
+def test_distributed_spp_split_reduce_gloo(tmp_path):
+    """N > 1 path on CPU: two gloo ranks each render their spp share (CPU oracle as the stand-in renderer for the
+    host logic), one reduce(sum) to rank 0, normalise: equals the single-rank render of all samples."""
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        import numpy as np, torch, torch.distributed as dist
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "tests"))
+        import parity
+        pkg = parity.pkg()
+        dist.init_process_group("gloo")
+        rank, ws = dist.get_rank(), dist.get_world_size()
+        world, st, flat = parity.load_scene("cornell", 24, 14, 6)
+        sc = parity.oracle_scene(flat)
+        count, offset = pkg.split_spp(st.min_samples, ws, rank)
+        film, _ = sc.render_pt(st.params(seed=3, spp=count, spp_offset=offset, spp_total=0))
+        t = torch.from_numpy(film.copy())
+        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            whole, _ = sc.render_pt(st.params(seed=3, spp=st.min_samples, spp_offset=0, spp_total=st.min_samples))
+            got = t.numpy() / st.min_samples
+            assert np.allclose(got, whole, rtol=1e-5, atol=1e-8), float(np.abs(got - whole).max())
+            print("REDUCE_OK")
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "REDUCE_OK" in out.stdout
