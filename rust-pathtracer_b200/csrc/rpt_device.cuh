@@ -69,7 +69,12 @@ struct DevTexture {
 struct DevScene {
   // acceleration structure
   const DevNode *nodes;  // TLAS nodes first, then every BLAS
-  int32_t tlas_root;     // child-ref
+  // TLAS leaf table: .x = instance id, .y = mesh-local triangle id or RPT_NONE (whole instance),
+  // .z = global triangle index, .w = the instance's candidate order. Untransformed mesh instances are
+  // flattened into the TLAS triangle by triangle (exact: their local space IS world space), so the common
+  // "one big untransformed mesh" scene traverses a single-level tree.
+  const uint4 *tlas_leaves;
+  int32_t tlas_root;     // child-ref (leaf refs index tlas_leaves)
   uint32_t num_instances;
   const DevInstance *instances;
   const float4 *tri_verts;    // 3 float4 per triangle: p0|material, p1|order, p2|unused  (w lanes as bits)
@@ -389,7 +394,7 @@ __device__ __forceinline__ bool slab_test(float3 bmin, float3 bmax, float3 oinv,
   float tz0 = fmaf(bmin.z, inv_d.z, -oinv.z), tz1 = fmaf(bmax.z, inv_d.z, -oinv.z);
   float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
   float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
-  tf *= 1.0000004f;  // 1 + 2*gamma(3)
+  tf *= 1.000001f;  // >= 1 + 2*gamma(3), plus headroom for the ~1 ulp reciprocal
   tnear = tn;
   return tn <= tf;
 }
@@ -410,7 +415,6 @@ __device__ __forceinline__ uint64_t tie_key(bool strict, uint32_t inst_order, ui
 }
 
 #define RPT_STACK_SIZE 64
-#define RPT_SENTINEL 0x7FFFFFFF
 
 // Two-level closest-hit traversal (replaces World::hit -> Accelerator::hit -> FlatBVH::traverse ->
 // Instance::hit -> Mesh::hit; world/mod.rs:166, accelerator/mod.rs:86-178, lbvh.rs:172-213,
@@ -421,6 +425,15 @@ __device__ __forceinline__ uint64_t tie_key(bool strict, uint32_t inst_order, ui
 struct TraceWork {
   uint32_t nodes, tris, insts;
 };
+
+#define RPT_DONE ((int)0x80000000)
+
+// 1/x for the slab test only (MUFU.RCP, ~1 ulp): it orders and prunes, it never decides a hit.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 template <bool ANY_HIT>
 __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d, float tmax, int *stack, int stride, TraceHit &out,
@@ -433,15 +446,33 @@ __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d,
   out.prim = RPT_NONE;
 
   float3 ro = o, rd = d;
-  float3 inv = f3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+  float3 inv = f3(rcp_approx(rd.x), rcp_approx(rd.y), rcp_approx(rd.z));
   float3 oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
-  int sp = 0;
+  int sp = 0, blas_base = 0;
   int cur = S.tlas_root;
   uint32_t cur_inst = RPT_NONE;  // != NONE while inside a BLAS
   uint32_t cur_inst_order = 0, cur_tri_base = 0;
 
+  // Pops the next node ref; leaving a BLAS (its stack segment is exhausted) restores the world-space ray.
+  auto pop = [&]() -> int {
+    if (cur_inst != RPT_NONE && sp == blas_base) {
+      ro = o;
+      rd = d;
+      inv = f3(rcp_approx(rd.x), rcp_approx(rd.y), rcp_approx(rd.z));
+      oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+      cur_inst = RPT_NONE;
+    }
+    if (sp == 0) return RPT_DONE;
+    --sp;
+    return stack[sp * stride];
+  };
+
+  // "while-while" traversal: the inner loop keeps every lane of the warp on the node-test code until each
+  // has reached a leaf (or run out of work); leaves are then processed together. Structured this way the
+  // warp reconverges at the end of the inner loop instead of drifting apart iteration by iteration.
   while (true) {
-    if (cur >= 0 && cur != RPT_SENTINEL) {
+    // ---- phase 1: descend through inner nodes (inner refs are >= 0)
+    while (cur >= 0) {
       work.nodes++;
       const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
       float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
@@ -451,31 +482,37 @@ __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d,
       bool hr = slab_test(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), oinv, inv, closest, tr);
       if (hl && hr) {
         bool left_first = tl <= tr;
-        int near_c = left_first ? ch.x : ch.y, far_c = left_first ? ch.y : ch.x;
-        stack[sp * stride] = far_c;
+        stack[sp * stride] = left_first ? ch.y : ch.x;
         ++sp;
-        cur = near_c;
-        continue;
-      } else if (hl) {
-        cur = ch.x;
-        continue;
-      } else if (hr) {
-        cur = ch.y;
-        continue;
+        cur = left_first ? ch.x : ch.y;
+      } else if (hl || hr) {
+        cur = hl ? ch.x : ch.y;
+      } else {
+        cur = pop();
       }
-    } else if (cur == RPT_SENTINEL) {
-      // leaving a BLAS: back to the world-space ray
-      ro = o;
-      rd = d;
-      inv = f3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
-      oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
-      cur_inst = RPT_NONE;
+    }
+    if (cur == RPT_DONE) break;
+
+    // ---- phase 2: a leaf
+    uint32_t idx = (uint32_t)(~cur);
+    bool is_tri = true;
+    uint32_t tri = 0, tri_local = idx, hit_inst = cur_inst, inst_order = cur_inst_order;
+    int next = 0;
+    bool have_next = false;
+    if (cur_inst != RPT_NONE) {
+      tri = cur_tri_base + idx;  // BLAS leaf: a triangle of the current mesh instance
     } else {
-      uint32_t idx = (uint32_t)(~cur);
-      if (cur_inst == RPT_NONE) {
-        // TLAS leaf: an instance
+      uint4 lf = __ldg(S.tlas_leaves + idx);
+      hit_inst = lf.x;
+      inst_order = lf.w;
+      if (lf.y != RPT_NONE) {
+        tri_local = lf.y;  // flattened triangle of an untransformed mesh instance: world ray as is
+        tri = lf.z;
+      } else {
+        // TLAS leaf: a whole instance
+        is_tri = false;
         work.insts++;
-        const DevInstance &I = S.instances[idx];
+        const DevInstance &I = S.instances[hit_inst];
         uint32_t flags = I.flags;
         float3 lo = o, ld = d;
         if (flags & DI_HAS_TRANSFORM) {  // instance.rs:89-95: direction is NOT renormalised, t is shared
@@ -484,64 +521,62 @@ __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d,
         }
         uint32_t kind = flags & DI_KIND_MASK;
         if (kind == RPT_AGG_MESH) {
-          stack[sp * stride] = RPT_SENTINEL;
-          ++sp;
+          blas_base = sp;
           ro = lo;
           rd = ld;
-          inv = f3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+          inv = f3(rcp_approx(rd.x), rcp_approx(rd.y), rcp_approx(rd.z));
           oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
-          cur_inst = idx;
-          cur_inst_order = I.order;
+          cur_inst = hit_inst;
+          cur_inst_order = inst_order;
           cur_tri_base = I.tri_base;
-          cur = I.blas_root;
-          continue;
-        }
-        float t;
-        bool hit;
-        // closest-so-far is passed as t1 exactly as the reference's candidate loop does; a candidate
-        // that passes with t == closest is resolved by tie_key (a strict sphere never gets that far).
-        if (kind == RPT_AGG_RECT)
-          hit = rect_test(I, lo, ld, 0.0f, closest, tmax, t);
-        else if (kind == RPT_AGG_SPHERE)
-          hit = sphere_test(I, lo, ld, 0.0f, closest, tmax, t);
-        else
-          hit = disk_test(I, lo, ld, 0.0f, closest, tmax, t);
-        if (hit) {
-          uint64_t key = tie_key(kind == RPT_AGG_SPHERE, I.order, 0);
-          if (!found || t < closest || key > best_key) {
-            closest = t;
-            best_key = key;
-            found = true;
-            out.t = t;
-            out.inst = idx;
-            out.prim = 0;
-            if (ANY_HIT) return true;
-          }
-        }
-      } else {
-        // BLAS leaf: a triangle of the current mesh instance
-        work.tris++;
-        uint32_t tri = cur_tri_base + idx;
-        const float4 *tv = S.tri_verts + 3 * (size_t)tri;
-        float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
-        float t, b0, b1, b2;
-        if (tri_test(f3(v0), f3(v1), f3(v2), ro, rd, 0.0f, closest, t, b0, b1, b2)) {
-          uint64_t key = tie_key(false, cur_inst_order, __float_as_uint(v1.w));
-          if (!found || t < closest || key > best_key) {
-            closest = t;
-            best_key = key;
-            found = true;
-            out.t = t;
-            out.inst = cur_inst;
-            out.prim = idx;
-            if (ANY_HIT) return true;
+          next = I.blas_root;
+          have_next = true;
+        } else {
+          float t;
+          bool hit;
+          // closest-so-far is passed as t1 exactly as the reference's candidate loop does; a candidate
+          // that passes with t == closest is resolved by tie_key (a strict sphere never gets that far).
+          if (kind == RPT_AGG_RECT)
+            hit = rect_test(I, lo, ld, 0.0f, closest, tmax, t);
+          else if (kind == RPT_AGG_SPHERE)
+            hit = sphere_test(I, lo, ld, 0.0f, closest, tmax, t);
+          else
+            hit = disk_test(I, lo, ld, 0.0f, closest, tmax, t);
+          if (hit) {
+            uint64_t key = tie_key(kind == RPT_AGG_SPHERE, inst_order, 0);
+            if (!found || t < closest || key > best_key) {
+              closest = t;
+              best_key = key;
+              found = true;
+              out.t = t;
+              out.inst = hit_inst;
+              out.prim = 0;
+              if (ANY_HIT) return true;
+            }
           }
         }
       }
     }
-    if (sp == 0) break;
-    --sp;
-    cur = stack[sp * stride];
+    if (is_tri) {
+      work.tris++;
+      const float4 *tv = S.tri_verts + 3 * (size_t)tri;
+      float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
+      float t, b0, b1, b2;
+      if (tri_test(f3(v0), f3(v1), f3(v2), ro, rd, 0.0f, closest, t, b0, b1, b2)) {
+        uint64_t key = tie_key(false, inst_order, __float_as_uint(v1.w));
+        if (!found || t < closest || key > best_key) {
+          closest = t;
+          best_key = key;
+          found = true;
+          out.t = t;
+          out.inst = hit_inst;
+          out.prim = tri_local;
+          if (ANY_HIT) return true;
+        }
+      }
+    }
+    cur = have_next ? next : pop();
+    if (cur == RPT_DONE) break;
   }
   return found;
 }

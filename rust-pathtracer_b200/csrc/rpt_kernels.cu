@@ -1008,8 +1008,33 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
       world.mx[k] = std::fmax(world.mx[k], b.mx[k]);
     }
   }
-  rpt::BuiltBvh tlas = rpt::build_bvh(ibox);
-  if (tlas.max_depth + max_blas_depth + 4 > RPT_STACK_SIZE)
+  // Reference-order TLAS over the instance boxes: gives every instance its candidate order (tie-breaks).
+  rpt::BuiltBvh ref_tlas = rpt::build_bvh(ibox);
+  // Device TLAS: instances, except that an untransformed mesh instance contributes its triangles directly.
+  std::vector<uint4> leaves;
+  std::vector<rpt::Box> leaf_box;
+  std::vector<char> flattened(d->num_instances, 0);
+  for (uint32_t i = 0; i < d->num_instances; ++i) {
+    const RptInstance &I = d->instances[i];
+    if (I.kind == RPT_AGG_MESH && !I.has_transform) {
+      const RptMesh &M = d->meshes[I.mesh];
+      flattened[i] = 1;
+      for (uint32_t t = 0; t < M.num_faces; ++t) {
+        float pts[9];
+        for (int k = 0; k < 3; ++k) std::memcpy(pts + 3 * k, M.vertices + 3 * (size_t)M.indices[3 * t + k], 3 * sizeof(float));
+        leaves.push_back(make_uint4(i, t, minfo[I.mesh].tri_base + t, ref_tlas.order[i]));
+        leaf_box.push_back(box_of_points(pts, 3));
+      }
+    } else {
+      leaves.push_back(make_uint4(i, RPT_NONE, 0, ref_tlas.order[i]));
+      leaf_box.push_back(ibox[i]);
+    }
+  }
+  rpt::BuiltBvh tlas = rpt::build_bvh(leaf_box);
+  uint32_t needed_blas_depth = 0;
+  for (uint32_t i = 0; i < d->num_instances; ++i)
+    if (d->instances[i].kind == RPT_AGG_MESH && !flattened[i]) needed_blas_depth = std::max(needed_blas_depth, minfo[d->instances[i].mesh].depth);
+  if (tlas.max_depth + needed_blas_depth + 4 > RPT_STACK_SIZE)
     return bail(fail("BVH deeper than the traversal stack (RPT_STACK_SIZE)"));
   for (auto &hn : tlas.nodes) nodes.push_back(to_dev_node(hn, 0));
   S->stats.tlas_nodes = tlas.nodes.size();
@@ -1035,7 +1060,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     D.size1 = I.size[1];
     D.flags = (I.kind & DI_KIND_MASK) | ((I.axis & 3u) << DI_AXIS_SHIFT) | (I.two_sided ? DI_TWO_SIDED : 0u) | (I.has_transform ? DI_HAS_TRANSFORM : 0u);
     D.material = I.material;
-    D.order = tlas.order[i];
+    D.order = ref_tlas.order[i];
     if (I.kind == RPT_AGG_MESH) {
       D.blas_root = mesh_root[I.mesh];
       D.tri_base = minfo[I.mesh].tri_base;
@@ -1053,6 +1078,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   int rc = 0;
   rc |= B.upload(nodes.data(), nodes.size(), &D.nodes);
   rc |= B.upload(insts.data(), insts.size(), &D.instances);
+  rc |= B.upload(leaves.data(), leaves.size(), &D.tlas_leaves);
   rc |= B.upload(tri_verts.data(), tri_verts.size(), &D.tri_verts);
   rc |= B.upload(tri_normals.data(), tri_normals.size(), &D.tri_normals);
   rc |= B.upload(d->lights, d->num_lights, &D.lights);
