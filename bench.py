@@ -37,7 +37,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "path_segments_per_sec"
 UNIT = "segments/s"
 SCENE = "cornell"
-CPU_SAMPLE = (480, 270)  # bounded CPU sample: same scene/spp/bounces, 1/16 of the pixels
+CPU_SAMPLE = (960, 540)  # bounded CPU sample: same scene/spp/bounces, 1/4 of the pixels (~2-3 s per pass on 16 cores)
 
 
 def load_peaks():
@@ -121,7 +121,7 @@ def run_reference(args):
     steps, warmup = args.steps, min(args.warmup, 1)
     _, st, _ = parity.load_scene(SCENE)
     value, sec_per_step, threads, cnt = cpu_oracle_run(parity, st.min_samples, steps, warmup)
-    sample = f"{SCENE} {CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} @ {st.min_samples} spp per step (1/16 of the 1080p frame's pixels, same bounces / light samples)"
+    sample = f"{SCENE} {CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} @ {st.min_samples} spp per step (1/4 of the 1080p frame's pixels, same bounces / light samples)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -295,9 +295,9 @@ def main():
 
     cpu = None
     if world_size == 1 and not args.no_cpu_baseline:
-        v, sec, threads, _ = cpu_oracle_run(parity, spp, 1, 0)
+        v, sec, threads, _ = cpu_oracle_run(parity, spp, 4, 0)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.scene} {CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} @ {spp} spp, one pass ({sec:.1f} s): 1/16 of the frame's pixels, same bounces / light samples; "
+               "sample": f"{args.scene} {CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} @ {spp} spp, 4 passes of {sec:.1f} s: 1/4 of the frame's pixels, same bounces / light samples; "
                          "C++/OpenMP oracle restatement (the Rust reference cannot be built in this image)"}
 
     ref_rays = c.camera_rays + c.bounce_rays + c.shadow_rays + c.light_rays

@@ -435,150 +435,223 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-template <bool ANY_HIT>
-__device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d, float tmax, int *stack, int stride, TraceHit &out,
-                                          TraceWork &work) {
-  float closest = tmax;
-  uint64_t best_key = 0;
-  bool found = false;
-  out.t = RPT_INF;
-  out.inst = RPT_NONE;
-  out.prim = RPT_NONE;
+// Watertight-test constants that depend only on the ray (mesh.rs:76-100 computes them per triangle; hoisting
+// them is exact: same inputs, same roundings).
+struct TriRay {
+  uint32_t kz;
+  float sx, sy, sz;
+};
+__device__ __forceinline__ TriRay tri_ray_setup(float3 d) {
+  TriRay r;
+  float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  float mx = fmaxf(fmaxf(ax, ay), az);
+  r.kz = 0;
+  if (ay >= mx) r.kz = 1;
+  if (az >= mx) r.kz = 2;  // ties -> highest axis index (mesh.rs:80-85)
+  float3 dd = tri_shuffle(d, r.kz);
+  r.sx = -dd.x / dd.z;
+  r.sy = -dd.y / dd.z;
+  r.sz = 1.0f / dd.z;
+  return r;
+}
+// MeshTriangleRef::hit with the per-ray part precomputed; identical arithmetic to tri_test().
+__device__ __forceinline__ bool tri_test_pre(float3 p0, float3 p1, float3 p2, float3 o, const TriRay &tr, float t0, float t1, float &t_out,
+                                             float &b0, float &b1, float &b2) {
+  float3 p0t = tri_shuffle(p0 - o, tr.kz), p1t = tri_shuffle(p1 - o, tr.kz), p2t = tri_shuffle(p2 - o, tr.kz);
+  p0t.x = __fadd_rn(p0t.x, __fmul_rn(tr.sx, p0t.z));
+  p1t.x = __fadd_rn(p1t.x, __fmul_rn(tr.sx, p1t.z));
+  p2t.x = __fadd_rn(p2t.x, __fmul_rn(tr.sx, p2t.z));
+  p0t.y = __fadd_rn(p0t.y, __fmul_rn(tr.sy, p0t.z));
+  p1t.y = __fadd_rn(p1t.y, __fmul_rn(tr.sy, p1t.z));
+  p2t.y = __fadd_rn(p2t.y, __fmul_rn(tr.sy, p2t.z));
+  float e0 = __fsub_rn(__fmul_rn(p1t.x, p2t.y), __fmul_rn(p1t.y, p2t.x));
+  float e1 = __fsub_rn(__fmul_rn(p2t.x, p0t.y), __fmul_rn(p2t.y, p0t.x));
+  float e2 = __fsub_rn(__fmul_rn(p0t.x, p1t.y), __fmul_rn(p0t.y, p1t.x));
+  if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+    e0 = (float)__dsub_rn(__dmul_rn((double)p2t.y, (double)p1t.x), __dmul_rn((double)p2t.x, (double)p1t.y));
+    e1 = (float)__dsub_rn(__dmul_rn((double)p0t.y, (double)p2t.x), __dmul_rn((double)p0t.x, (double)p2t.y));
+    e2 = (float)__dsub_rn(__dmul_rn((double)p1t.y, (double)p0t.x), __dmul_rn((double)p1t.x, (double)p0t.y));
+  }
+  if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+  float det = __fadd_rn(__fadd_rn(e0, e1), e2);
+  if (det == 0.0f) return false;
+  float z0 = __fmul_rn(p0t.z, tr.sz), z1 = __fmul_rn(p1t.z, tr.sz), z2 = __fmul_rn(p2t.z, tr.sz);
+  float t_scaled = __fadd_rn(__fadd_rn(__fmul_rn(e0, z0), __fmul_rn(e1, z1)), __fmul_rn(e2, z2));
+  float lo = __fmul_rn(t0, det), hi = __fmul_rn(t1, det);
+  if ((det < 0.0f && (t_scaled >= lo || t_scaled < hi)) || (det > 0.0f && (t_scaled <= lo || t_scaled > hi))) return false;
+  float inv_det = 1.0f / det;
+  b0 = __fmul_rn(e0, inv_det);
+  b1 = __fmul_rn(e1, inv_det);
+  b2 = __fmul_rn(e2, inv_det);
+  t_out = __fmul_rn(t_scaled, inv_det);
+  return true;
+}
 
-  float3 ro = o, rd = d;
-  float3 inv = f3(rcp_approx(rd.x), rcp_approx(rd.y), rcp_approx(rd.z));
-  float3 oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
-  int sp = 0, blas_base = 0;
-  int cur = S.tlas_root;
-  uint32_t cur_inst = RPT_NONE;  // != NONE while inside a BLAS
-  uint32_t cur_inst_order = 0, cur_tri_base = 0;
+// Two-level closest-hit traversal (replaces World::hit -> Accelerator::hit -> FlatBVH::traverse ->
+// Instance::hit -> Mesh::hit; world/mod.rs:166, accelerator/mod.rs:86-178, lbvh.rs:172-213,
+// instance.rs:75-133, mesh.rs:314-360). Unlike the reference (F8) it prunes by the closest hit so far;
+// results are identical because pruned boxes cannot contain a closer hit. State lives in registers.
+struct Trav {
+  float3 o, d;       // world-space ray
+  float3 ro, rd;     // current-space ray (instance-local inside a BLAS)
+  float3 inv, oinv;  // slab-test reciprocals of the current-space ray
+  TriRay tr;         // watertight-test constants of the current-space ray
+  float tmax, closest;
+  uint64_t best_key;
+  int cur, sp, blas_base;
+  uint32_t cur_inst, cur_inst_order, cur_tri_base;
+  bool found;
+  TraceHit out;
 
+  __device__ __forceinline__ void set_space(float3 no, float3 nd) {
+    ro = no;
+    rd = nd;
+    inv = f3(rcp_approx(rd.x), rcp_approx(rd.y), rcp_approx(rd.z));
+    oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+    tr = tri_ray_setup(rd);
+  }
+  __device__ __forceinline__ void init(const DevScene &S, float3 o_, float3 d_, float tmax_) {
+    o = o_;
+    d = d_;
+    tmax = closest = tmax_;
+    best_key = 0;
+    found = false;
+    out.t = RPT_INF;
+    out.inst = RPT_NONE;
+    out.prim = RPT_NONE;
+    sp = 0;
+    blas_base = 0;
+    cur = S.tlas_root;
+    cur_inst = RPT_NONE;
+    cur_inst_order = cur_tri_base = 0;
+    set_space(o, d);
+  }
   // Pops the next node ref; leaving a BLAS (its stack segment is exhausted) restores the world-space ray.
-  auto pop = [&]() -> int {
+  __device__ __forceinline__ int pop(const int *stack, int stride) {
     if (cur_inst != RPT_NONE && sp == blas_base) {
-      ro = o;
-      rd = d;
-      inv = f3(rcp_approx(rd.x), rcp_approx(rd.y), rcp_approx(rd.z));
-      oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+      set_space(o, d);
       cur_inst = RPT_NONE;
     }
     if (sp == 0) return RPT_DONE;
     --sp;
     return stack[sp * stride];
-  };
-
-  // "while-while" traversal: the inner loop keeps every lane of the warp on the node-test code until each
-  // has reached a leaf (or run out of work); leaves are then processed together. Structured this way the
-  // warp reconverges at the end of the inner loop instead of drifting apart iteration by iteration.
-  while (true) {
-    // ---- phase 1: descend through inner nodes (inner refs are >= 0)
-    while (cur >= 0) {
-      work.nodes++;
-      const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
-      float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-      int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
-      float tl, tr;
-      bool hl = slab_test(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), oinv, inv, closest, tl);
-      bool hr = slab_test(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), oinv, inv, closest, tr);
-      if (hl && hr) {
-        bool left_first = tl <= tr;
-        stack[sp * stride] = left_first ? ch.y : ch.x;
-        ++sp;
-        cur = left_first ? ch.x : ch.y;
-      } else if (hl || hr) {
-        cur = hl ? ch.x : ch.y;
-      } else {
-        cur = pop();
-      }
+  }
+  __device__ __forceinline__ void accept(float t, uint64_t key, uint32_t inst, uint32_t prim) {
+    if (!found || t < closest || key > best_key) {
+      closest = t;
+      best_key = key;
+      found = true;
+      out.t = t;
+      out.inst = inst;
+      out.prim = prim;
     }
-    if (cur == RPT_DONE) break;
+  }
 
-    // ---- phase 2: a leaf
-    uint32_t idx = (uint32_t)(~cur);
-    bool is_tri = true;
-    uint32_t tri = 0, tri_local = idx, hit_inst = cur_inst, inst_order = cur_inst_order;
-    int next = 0;
-    bool have_next = false;
-    if (cur_inst != RPT_NONE) {
-      tri = cur_tri_base + idx;  // BLAS leaf: a triangle of the current mesh instance
-    } else {
-      uint4 lf = __ldg(S.tlas_leaves + idx);
-      hit_inst = lf.x;
-      inst_order = lf.w;
-      if (lf.y != RPT_NONE) {
-        tri_local = lf.y;  // flattened triangle of an untransformed mesh instance: world ray as is
-        tri = lf.z;
-      } else {
-        // TLAS leaf: a whole instance
-        is_tri = false;
-        work.insts++;
-        const DevInstance &I = S.instances[hit_inst];
-        uint32_t flags = I.flags;
-        float3 lo = o, ld = d;
-        if (flags & DI_HAS_TRANSFORM) {  // instance.rs:89-95: direction is NOT renormalised, t is shared
-          lo = xform_point(I.rev, o);
-          ld = xform_vec(I.rev, d);
-        }
-        uint32_t kind = flags & DI_KIND_MASK;
-        if (kind == RPT_AGG_MESH) {
-          blas_base = sp;
-          ro = lo;
-          rd = ld;
-          inv = f3(rcp_approx(rd.x), rcp_approx(rd.y), rcp_approx(rd.z));
-          oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
-          cur_inst = hit_inst;
-          cur_inst_order = inst_order;
-          cur_tri_base = I.tri_base;
-          next = I.blas_root;
-          have_next = true;
+  // "while-while": the inner loop keeps every lane of the warp on the node-test code until each has reached a
+  // leaf (or run out of work); leaves are then processed together, so the warp reconverges at the end of the
+  // inner loop instead of drifting apart iteration by iteration.
+  template <bool ANY_HIT>
+  __device__ __forceinline__ void run(const DevScene &S, int *stack, int stride, TraceWork &work) {
+    while (true) {
+      // ---- phase 1: descend through inner nodes (inner refs are >= 0)
+      while (cur >= 0) {
+        work.nodes++;
+        const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
+        float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+        int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
+        float tl, trr;
+        bool hl = slab_test(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), oinv, inv, closest, tl);
+        bool hr = slab_test(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), oinv, inv, closest, trr);
+        if (hl && hr) {
+          bool left_first = tl <= trr;
+          stack[sp * stride] = left_first ? ch.y : ch.x;
+          ++sp;
+          cur = left_first ? ch.x : ch.y;
+        } else if (hl || hr) {
+          cur = hl ? ch.x : ch.y;
         } else {
-          float t;
-          bool hit;
-          // closest-so-far is passed as t1 exactly as the reference's candidate loop does; a candidate
-          // that passes with t == closest is resolved by tie_key (a strict sphere never gets that far).
-          if (kind == RPT_AGG_RECT)
-            hit = rect_test(I, lo, ld, 0.0f, closest, tmax, t);
-          else if (kind == RPT_AGG_SPHERE)
-            hit = sphere_test(I, lo, ld, 0.0f, closest, tmax, t);
-          else
-            hit = disk_test(I, lo, ld, 0.0f, closest, tmax, t);
-          if (hit) {
-            uint64_t key = tie_key(kind == RPT_AGG_SPHERE, inst_order, 0);
-            if (!found || t < closest || key > best_key) {
-              closest = t;
-              best_key = key;
-              found = true;
-              out.t = t;
-              out.inst = hit_inst;
-              out.prim = 0;
-              if (ANY_HIT) return true;
+          cur = pop(stack, stride);
+        }
+      }
+      if (cur == RPT_DONE) return;
+
+      // ---- phase 2: a leaf
+      uint32_t idx = (uint32_t)(~cur);
+      bool is_tri = true;
+      uint32_t tri = 0, tri_local = idx, hit_inst = cur_inst, inst_order = cur_inst_order;
+      int next = 0;
+      bool have_next = false;
+      if (cur_inst != RPT_NONE) {
+        tri = cur_tri_base + idx;  // BLAS leaf: a triangle of the current mesh instance
+      } else {
+        uint4 lf = __ldg(S.tlas_leaves + idx);
+        hit_inst = lf.x;
+        inst_order = lf.w;
+        if (lf.y != RPT_NONE) {
+          tri_local = lf.y;  // flattened triangle of an untransformed mesh instance: world ray as is
+          tri = lf.z;
+        } else {
+          // TLAS leaf: a whole instance
+          is_tri = false;
+          work.insts++;
+          const DevInstance &I = S.instances[hit_inst];
+          uint32_t flags = I.flags;
+          float3 lo = o, ld = d;
+          if (flags & DI_HAS_TRANSFORM) {  // instance.rs:89-95: direction is NOT renormalised, t is shared
+            lo = xform_point(I.rev, o);
+            ld = xform_vec(I.rev, d);
+          }
+          uint32_t kind = flags & DI_KIND_MASK;
+          if (kind == RPT_AGG_MESH) {
+            blas_base = sp;
+            set_space(lo, ld);
+            cur_inst = hit_inst;
+            cur_inst_order = inst_order;
+            cur_tri_base = I.tri_base;
+            next = I.blas_root;
+            have_next = true;
+          } else {
+            float t;
+            bool hit;
+            // closest-so-far is passed as t1 exactly as the reference's candidate loop does; a candidate
+            // that passes with t == closest is resolved by tie_key (a strict sphere never gets that far).
+            if (kind == RPT_AGG_RECT)
+              hit = rect_test(I, lo, ld, 0.0f, closest, tmax, t);
+            else if (kind == RPT_AGG_SPHERE)
+              hit = sphere_test(I, lo, ld, 0.0f, closest, tmax, t);
+            else
+              hit = disk_test(I, lo, ld, 0.0f, closest, tmax, t);
+            if (hit) {
+              accept(t, tie_key(kind == RPT_AGG_SPHERE, inst_order, 0), hit_inst, 0);
+              if (ANY_HIT) return;
             }
           }
         }
       }
-    }
-    if (is_tri) {
-      work.tris++;
-      const float4 *tv = S.tri_verts + 3 * (size_t)tri;
-      float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
-      float t, b0, b1, b2;
-      if (tri_test(f3(v0), f3(v1), f3(v2), ro, rd, 0.0f, closest, t, b0, b1, b2)) {
-        uint64_t key = tie_key(false, inst_order, __float_as_uint(v1.w));
-        if (!found || t < closest || key > best_key) {
-          closest = t;
-          best_key = key;
-          found = true;
-          out.t = t;
-          out.inst = hit_inst;
-          out.prim = tri_local;
-          if (ANY_HIT) return true;
+      if (is_tri) {
+        work.tris++;
+        const float4 *tv = S.tri_verts + 3 * (size_t)tri;
+        float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
+        float t, b0, b1, b2;
+        if (tri_test_pre(f3(v0), f3(v1), f3(v2), ro, tr, 0.0f, closest, t, b0, b1, b2)) {
+          accept(t, tie_key(false, inst_order, __float_as_uint(v1.w)), hit_inst, tri_local);
+          if (ANY_HIT) return;
         }
       }
+      cur = have_next ? next : pop(stack, stride);
+      if (cur == RPT_DONE) return;
     }
-    cur = have_next ? next : pop();
-    if (cur == RPT_DONE) break;
   }
-  return found;
+};
+
+template <bool ANY_HIT>
+__device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d, float tmax, int *stack, int stride, TraceHit &out,
+                                          TraceWork &work) {
+  Trav t;
+  t.init(S, o, d, tmax);
+  t.template run<ANY_HIT>(S, stack, stride, work);
+  out = t.out;
+  return t.found;
 }
 
 // Full hit record of a known (instance, primitive, t): Instance::hit's output (instance.rs:96-116).

@@ -120,6 +120,9 @@ __device__ __forceinline__ uint32_t warp_append_n(uint32_t *counter, uint32_t n)
 }
 
 #define TRACE_THREADS 128
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 8  // resident CTAs per SM the traversal kernels are compiled for (register cap = 65536 / (128 * this))
+#endif
 
 // per-thread BVH work counters -> one 64-bit atomic per warp per counter at kernel end
 __device__ __forceinline__ void flush_work(const TraceWork &w, unsigned long long *work) {
@@ -175,11 +178,11 @@ __device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t m
 }
 
 // Closest-hit traversal of the path queue; appends each path to the list of its vertex's class.
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
                                                          uint32_t *__restrict__ q_miss, uint32_t *__restrict__ q_diffuse,
                                                          uint32_t *__restrict__ q_ggx, uint32_t *__restrict__ counts,
                                                          unsigned long long *__restrict__ work) {
-  __shared__ int s_stack[RPT_STACK_SIZE * TRACE_THREADS];
+  extern __shared__ int s_stack[];  // [stack entry][thread]; depth chosen per scene at rpt_scene_create
   TraceWork tw{0, 0, 0};
   const uint32_t n = counts[Q_PATHS];
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -452,10 +455,10 @@ __global__ void __launch_bounds__(128) k_shade_surface(DevScene S, RenderCtx R, 
 
 // NEE visibility. Light samples: closest hit, accepted when ANY light-material surface is hit, whose own
 // emission is used (pt.rs:177-218, F9). Environment samples: any hit kills the sample (pt.rs:254-263).
-__global__ void __launch_bounds__(TRACE_THREADS) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
                                                           const uint32_t *__restrict__ sh_c, const uint32_t *__restrict__ counts,
                                                           float *__restrict__ acc, unsigned long long *__restrict__ work) {
-  __shared__ int s_stack[RPT_STACK_SIZE * TRACE_THREADS];
+  extern __shared__ int s_stack[];
   TraceWork tw{0, 0, 0};
   const uint32_t n = counts[Q_SHADOW];
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -537,7 +540,7 @@ __global__ void k_scale(float4 *film, uint64_t n, float s) {
 // generic closest-hit query of host-provided rays (rpt_trace_rays)
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32_t n, const float *__restrict__ o, const float *__restrict__ d,
                                                               const float *__restrict__ tmax, HitRec *__restrict__ hits) {
-  __shared__ int s_stack[RPT_STACK_SIZE * TRACE_THREADS];
+  extern __shared__ int s_stack[];
   uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     TraceHit th;
@@ -595,6 +598,8 @@ struct RptScene {
   size_t film_pixels = 0;
   // launch geometry
   int grid[K_NUM] = {0};
+  uint32_t stack_entries = 16;
+  size_t stack_smem = 0;
   // timing of the last render
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -797,7 +802,7 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       uint32_t *cb = w.counts + (size_t)b * Q_COUNT, *cn = w.counts + (size_t)(b + 1) * Q_COUNT;
       PathRec *in = w.paths[b & 1], *out = w.paths[(b + 1) & 1];
       T.begin(K_TRACE);
-      k_trace<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work);
+      k_trace<<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work);
       T.end();
       T.begin(K_SHADE_MISS);
       k_shade_miss<<<S->grid[K_SHADE_MISS], 256, 0, S->stream>>>(S->dev, in, w.q_miss, cb, w.acc);
@@ -810,7 +815,7 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       T.end();
       if (P->light_samples > 0) {
         T.begin(K_SHADOW);
-        k_shadow<<<S->grid[K_SHADOW], TRACE_THREADS, 0, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc, w.work + 3);
+        k_shadow<<<S->grid[K_SHADOW], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc, w.work + 3);
         T.end();
       }
     }
@@ -1034,8 +1039,11 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   uint32_t needed_blas_depth = 0;
   for (uint32_t i = 0; i < d->num_instances; ++i)
     if (d->instances[i].kind == RPT_AGG_MESH && !flattened[i]) needed_blas_depth = std::max(needed_blas_depth, minfo[d->instances[i].mesh].depth);
-  if (tlas.max_depth + needed_blas_depth + 4 > RPT_STACK_SIZE)
-    return bail(fail("BVH deeper than the traversal stack (RPT_STACK_SIZE)"));
+  // one push per inner node on the path; shared-memory stack sized to the scene (16 / 32 / 64 / 128 entries per thread)
+  uint32_t need = tlas.max_depth + needed_blas_depth + 2;
+  S->stack_entries = need <= 16 ? 16 : (need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 0)));
+  if (S->stack_entries == 0) return bail(fail("BVH deeper than the largest traversal stack (128 entries)"));
+  S->stack_smem = (size_t)S->stack_entries * TRACE_THREADS * sizeof(int);
   for (auto &hn : tlas.nodes) nodes.push_back(to_dev_node(hn, 0));
   S->stats.tlas_nodes = tlas.nodes.size();
   std::vector<int32_t> mesh_root(d->num_meshes);
@@ -1149,11 +1157,16 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
       return bail(fail("num_lambda too large for the film kernel's shared-memory CIE tables"));
   }
   S->grid[K_RAYGEN] = occupancy_grid(k_raygen, 256, 0, S->num_sms);
-  S->grid[K_TRACE] = occupancy_grid(k_trace, TRACE_THREADS, 0, S->num_sms);
+  if (S->stack_smem > 48 * 1024) {
+    cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
+    cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
+    cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
+  }
+  S->grid[K_TRACE] = occupancy_grid(k_trace, TRACE_THREADS, S->stack_smem, S->num_sms);
   S->grid[K_SHADE_MISS] = occupancy_grid(k_shade_miss, 256, 0, S->num_sms);
   S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_surface<Q_DIFFUSE>, 128, 0, S->num_sms);
   S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_surface<Q_GGX>, 128, 0, S->num_sms);
-  S->grid[K_SHADOW] = occupancy_grid(k_shadow, TRACE_THREADS, 0, S->num_sms);
+  S->grid[K_SHADOW] = occupancy_grid(k_shadow, TRACE_THREADS, S->stack_smem, S->num_sms);
   S->grid[K_FILM] = occupancy_grid(k_film, 256, film_smem, S->num_sms);
   *out = S;
   return 0;
@@ -1199,7 +1212,7 @@ int rpt_trace_primary(RptScene *S, const RptRenderParams *P, uint32_t *inst, uin
   WaveBuffers &w = S->wave;
   CUDA_TRY(cudaMemsetAsync(w.counts, 0, (RPT_MAX_BOUNCES + 1) * Q_COUNT * sizeof(uint32_t), S->stream));
   k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
-  k_trace<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts, w.work);
+  k_trace<<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts, w.work);
   std::vector<HitRec> h(wh);
   CUDA_TRY(cudaMemcpyAsync(h.data(), w.hits, wh * sizeof(HitRec), cudaMemcpyDeviceToHost, S->stream));
   CUDA_TRY(cudaStreamSynchronize(S->stream));
@@ -1225,7 +1238,7 @@ int rpt_trace_rays(RptScene *S, uint32_t n, const float *origins, const float *d
   CUDA_TRY(cudaMemcpyAsync(d_o, origins, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
   CUDA_TRY(cudaMemcpyAsync(d_d, dirs, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
   CUDA_TRY(cudaMemcpyAsync(d_t, tmax, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
-  k_trace_rays<<<S->grid[K_TRACE], TRACE_THREADS, 0, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
+  k_trace_rays<<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
   std::vector<HitRec> h(n);
   CUDA_TRY(cudaMemcpyAsync(h.data(), d_h, (size_t)n * sizeof(HitRec), cudaMemcpyDeviceToHost, S->stream));
   CUDA_TRY(cudaStreamSynchronize(S->stream));

@@ -1,0 +1,20 @@
+#!/usr/bin/env python3
+"""Times library variants (librpt_var_*.so) on the bench workload: python tools/variant_bench.py <scene> <so>..."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import parity
+p = parity.pkg()
+name = sys.argv[1]
+world, st, flat = parity.load_scene(name)
+for so in sys.argv[2:]:
+    lib = p.ffi.load_library(os.path.join(p.ffi.PKG_DIR, so))
+    sc = p.ffi.Scene(lib, flat, 0)
+    best = None
+    for i in range(3):
+        ptr, cnt = sc.render_pt_device(st.params(seed=i, spp_total=0))
+        kt = {k["name"]: k["ms"] for k in sc.kernel_times()}
+        if best is None or cnt.device_ms < best[0]:
+            best = (cnt.device_ms, kt, cnt.segments)
+    print(f"{so:28s} {best[0]:8.2f} ms  {best[2] / best[0] / 1e6:6.3f} Gseg/s  trace {best[1].get('k_trace', 0):7.2f} shadow {best[1].get('k_shadow', 0):7.2f} shade {best[1].get('k_shade_surface<diffuse>', 0):7.2f} ggx {best[1].get('k_shade_surface<ggx>', 0):7.2f}")
+    sc.close()
