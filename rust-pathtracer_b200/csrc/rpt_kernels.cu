@@ -62,7 +62,12 @@ struct __align__(16) HitRec {
   uint32_t inst, prim, pad;
 };
 
-enum : uint32_t { Q_PATHS = 0, Q_MISS = 1, Q_DIFFUSE = 2, Q_GGX = 3, Q_SHADOW = 4, Q_NAN = 5, Q_SHADOW_REF = 6, Q_COUNT = 8 };
+// Per-bounce counters. Q_PATHS..Q_SHADOW are queue SIZES (they include the invalid entries that pad abandoned
+// chunk tails, see chunk_append); the N_* entries count valid items and feed the Profile counters.
+enum : uint32_t {
+  Q_PATHS = 0, Q_MISS = 1, Q_DIFFUSE = 2, Q_GGX = 3, Q_SHADOW = 4, Q_NAN = 5, Q_SHADOW_REF = 6,
+  N_PATHS = 7, N_MISS = 8, N_DIFFUSE = 9, N_GGX = 10, N_SHADOW = 11, Q_COUNT = 12
+};
 #define RPT_MAX_BOUNCES 64
 
 struct RenderCtx {
@@ -91,32 +96,56 @@ __device__ __forceinline__ float3 rec_origin(const PathRec &r) {
   return p + (n * RPT_NORMAL_OFFSET) * r.r3.y;
 }
 
-// warp-aggregated append: returns this lane's index in the queue, or RPT_NONE if !pred.
-__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
+// cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass L1 (.cg) and complete asynchronously.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Queue append without a global atomic per warp per iteration. Every warp owns a private chunk of QCHUNK
+// consecutive entries of the output queue and hands them out with ballot + popc; only when the chunk is used up
+// does one lane reserve the next chunk with a single atomicAdd on the queue size (ncu on the first version: 46 % of
+// the shade kernel's stall samples sat on the SHFL that waits for the per-warp atomic's return value).
+// The tail a warp abandons (at most 31 entries when a chunk overflows, the rest of the chunk at kernel end) is
+// filled with invalid markers (RPT_NONE in the entry's first id word); consumers skip them. Chunk tails are
+// contiguous, so whole warps of the consumer skip together.
+#define QCHUNK 256u
+struct WarpChunk {
+  uint32_t base, used;
+};
+__device__ __forceinline__ WarpChunk chunk_init() { return WarpChunk{0u, QCHUNK}; }
+template <class Mark>
+__device__ __forceinline__ void chunk_pad(const WarpChunk &wc, Mark mark) {
+  for (uint32_t e = wc.used + (threadIdx.x & 31u); e < QCHUNK; e += 32u) mark(wc.base + e);
+}
+// All 32 lanes must call. Returns this lane's entry index, or RPT_NONE if !pred.
+template <class Mark>
+__device__ __forceinline__ uint32_t chunk_append(uint32_t *counter, WarpChunk &wc, bool pred, Mark mark) {
   uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
   if (mask == 0) return RPT_NONE;
   uint32_t lane = threadIdx.x & 31u;
-  uint32_t leader = __ffs(mask) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(counter, __popc(mask));
-  base = __shfl_sync(0xFFFFFFFFu, base, leader);
-  return pred ? base + __popc(mask & ((1u << lane) - 1u)) : RPT_NONE;
-}
-// variable-count variant: each lane reserves `n` consecutive entries.
-__device__ __forceinline__ uint32_t warp_append_n(uint32_t *counter, uint32_t n) {
-  uint32_t lane = threadIdx.x & 31u;
-  uint32_t incl = n;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= (uint32_t)o) incl += v;
+  uint32_t cnt = __popc(mask);
+  if (wc.used + cnt > QCHUNK) {  // warp-uniform
+    chunk_pad(wc, mark);
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(counter, QCHUNK);
+    wc.base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    wc.used = 0;
   }
-  uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  uint32_t base = 0;
-  if (total == 0) return 0;
-  if (lane == 31) base = atomicAdd(counter, total);
-  base = __shfl_sync(0xFFFFFFFFu, base, 31);
-  return base + incl - n;
+  uint32_t idx = wc.base + wc.used + __popc(mask & ((1u << lane) - 1u));
+  wc.used += cnt;
+  return pred ? idx : RPT_NONE;
+}
+// per-thread statistics -> one atomic per warp at kernel end
+__device__ __forceinline__ void flush_count(uint32_t v, uint32_t *dst) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, v);
 }
 
 #define TRACE_THREADS 128
@@ -170,7 +199,10 @@ __global__ void __launch_bounds__(256) k_raygen(DevScene S, RenderCtx R, PathRec
     r.r3 = make_float4(__uint_as_float(slot), 0.0f, 0.0f, 0.0f);
     out[slot] = r;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) counts[Q_PATHS] = R.n_slots;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counts[Q_PATHS] = R.n_slots;
+    counts[N_PATHS] = R.n_slots;
+  }
 }
 
 __device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t material) {
@@ -184,19 +216,24 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
                                                          unsigned long long *__restrict__ work) {
   extern __shared__ int s_stack[];  // [stack entry][thread]; depth chosen per scene at rpt_scene_create
   TraceWork tw{0, 0, 0};
+  WarpChunk wc_miss = chunk_init(), wc_diffuse = chunk_init(), wc_ggx = chunk_init();
+  uint32_t n_miss = 0, n_diffuse = 0, n_ggx = 0;
   const uint32_t n = counts[Q_PATHS];
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t n_round = (n + 31u) & ~31u;  // keep whole warps in the loop for the ballots
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
     bool active = i < n;
     uint32_t cls = RPT_NONE;
+    PathRec r;
     if (active) {
       const float4 *rp = reinterpret_cast<const float4 *>(paths + i);
-      PathRec r;
       r.r0 = __ldg(rp);
       r.r1 = __ldg(rp + 1);
       r.r2 = __ldg(rp + 2);
       r.r3 = __ldg(rp + 3);
+      active = __float_as_uint(r.r3.x) != RPT_NONE;  // padding of an abandoned chunk tail
+    }
+    if (active) {
       float3 o = rec_origin(r), d = f3(r.r2);
       TraceHit th;
       bool hit = trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
@@ -219,13 +256,22 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
       }
     }
     uint32_t k;
-    k = warp_append(counts + Q_MISS, cls == Q_MISS);
+    k = chunk_append(counts + Q_MISS, wc_miss, cls == Q_MISS, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
     if (cls == Q_MISS) q_miss[k] = i;
-    k = warp_append(counts + Q_DIFFUSE, cls == Q_DIFFUSE);
+    k = chunk_append(counts + Q_DIFFUSE, wc_diffuse, cls == Q_DIFFUSE, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; });
     if (cls == Q_DIFFUSE) q_diffuse[k] = i;
-    k = warp_append(counts + Q_GGX, cls == Q_GGX);
+    k = chunk_append(counts + Q_GGX, wc_ggx, cls == Q_GGX, [&](uint32_t e) { q_ggx[e] = RPT_NONE; });
     if (cls == Q_GGX) q_ggx[k] = i;
+    n_miss += cls == Q_MISS;
+    n_diffuse += cls == Q_DIFFUSE;
+    n_ggx += cls == Q_GGX;
   }
+  if (wc_miss.used < QCHUNK) chunk_pad(wc_miss, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
+  if (wc_diffuse.used < QCHUNK) chunk_pad(wc_diffuse, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; });
+  if (wc_ggx.used < QCHUNK) chunk_pad(wc_ggx, [&](uint32_t e) { q_ggx[e] = RPT_NONE; });
+  flush_count(n_miss, counts + N_MISS);
+  flush_count(n_diffuse, counts + N_DIFFUSE);
+  flush_count(n_ggx, counts + N_GGX);
   flush_work(tw, work);
 }
 
@@ -236,6 +282,7 @@ __global__ void __launch_bounds__(256) k_shade_miss(DevScene S, const PathRec *_
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint32_t idx = queue[i];
+    if (idx == RPT_NONE) continue;  // chunk padding
     const float4 *rp = reinterpret_cast<const float4 *>(paths + idx);
     float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
     float3 wo = f3(r2);
@@ -254,22 +301,53 @@ __global__ void __launch_bounds__(256) k_shade_miss(DevScene S, const PathRec *_
 
 // One walk vertex of a material class: light-hit MIS (pt.rs:512-561), NEE generation
 // (pt.rs:562-604,333-393,146-219,224-331), BSDF sampling + russian roulette (integrator/utils.rs:214-329).
+#define SHADE_THREADS 128
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 6
+#endif
 template <uint32_t CLASS>
-__global__ void __launch_bounds__(128) k_shade_surface(DevScene S, RenderCtx R, uint32_t bounce, const PathRec *__restrict__ paths,
+__global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surface(DevScene S, RenderCtx R, uint32_t bounce, const PathRec *__restrict__ paths,
                                                        const HitRec *__restrict__ hits, const uint32_t *__restrict__ queue,
                                                        uint32_t *__restrict__ counts, uint32_t *__restrict__ next_counts,
                                                        PathRec *__restrict__ out, float4 *__restrict__ sh_a, float4 *__restrict__ sh_b,
                                                        uint32_t *__restrict__ sh_c, float *__restrict__ acc) {
+  // Software-pipelined gather: while item i is shaded, the path + hit record of item i + stride (80 B, reached
+  // through the class list) is already in flight to this thread's private shared-memory slot via cp.async, so the
+  // DRAM latency of the gather overlaps the shading arithmetic instead of stalling it (ncu v1: long-scoreboard
+  // 10 warps per issue). [stage][float4 k][thread]: consecutive threads hit consecutive 16-byte words.
+  __shared__ float4 s_stage[2][5][SHADE_THREADS];
   const uint32_t n = counts[CLASS];
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t n_round = (n + 31u) & ~31u;
   const uint32_t L = R.light_samples;
   const uint32_t max_bounces = R.only_direct ? 1u : R.max_bounces;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    bool active = i < n;
+  const uint32_t tid = threadIdx.x;
+  auto issue = [&](int stage, uint32_t idx) {
+    if (idx != RPT_NONE) {
+      const float4 *rp = reinterpret_cast<const float4 *>(paths + idx);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cp_async16(&s_stage[stage][k][tid], rp + k);
+      cp_async16(&s_stage[stage][4][tid], hits + idx);
+    }
+    cp_async_commit();
+  };
+  WarpChunk wc_next = chunk_init(), wc_shadow = chunk_init();
+  uint32_t n_next = 0, n_shadow = 0, n_sh_ref = 0, n_nan = 0;
+  auto mark_next = [&](uint32_t e) { out[e].r3 = make_float4(__uint_as_float(RPT_NONE), 0.0f, 0.0f, 0.0f); };
+  auto mark_shadow = [&](uint32_t e) { sh_c[e] = RPT_NONE; };
+  uint32_t i0 = blockIdx.x * blockDim.x + tid;
+  uint32_t idx_cur = i0 < n ? __ldg(queue + i0) : RPT_NONE;
+  uint32_t idx_next = i0 + stride < n ? __ldg(queue + i0 + stride) : RPT_NONE;
+  issue(0, idx_cur);
+  int stage = 0;
+  for (uint32_t i = i0; i < n_round; i += stride) {
+    issue(stage ^ 1, idx_next);  // prefetch the next item while this one is shaded
+    uint32_t i_nn = i + 2 * stride;
+    uint32_t idx_nn = i_nn < n ? __ldg(queue + i_nn) : RPT_NONE;
+    cp_async_wait<1>();  // everything but the group just committed has landed
+    bool active = idx_cur != RPT_NONE;  // beyond the queue, or chunk padding
     bool continues = false, do_nee = false;
     PathRec nr;
-    uint32_t n_sh_ref = 0;
     // state shared between the vertex evaluation and the warp-uniform NEE loop below
     SurfaceHit sh;
     Frame frame;
@@ -282,18 +360,16 @@ __global__ void __launch_bounds__(128) k_shade_surface(DevScene S, RenderCtx R, 
     gp.kappa = 0.0f;
     gp.metallic = false;
     if (active) {
-      uint32_t idx = queue[i];
-      const float4 *rp = reinterpret_cast<const float4 *>(paths + idx);
       PathRec r;
-      r.r0 = __ldg(rp);
-      r.r1 = __ldg(rp + 1);
-      r.r2 = __ldg(rp + 2);
-      r.r3 = __ldg(rp + 3);
-      HitRec hr = hits[idx];
+      r.r0 = s_stage[stage][0][tid];
+      r.r1 = s_stage[stage][1][tid];
+      r.r2 = s_stage[stage][2][tid];
+      r.r3 = s_stage[stage][3][tid];
+      float4 hraw = s_stage[stage][4][tid];
       TraceHit th;
-      th.t = hr.t;
-      th.inst = hr.inst;
-      th.prim = hr.prim;
+      th.t = hraw.x;
+      th.inst = __float_as_uint(hraw.y);
+      th.prim = __float_as_uint(hraw.z);
       float3 prev_p = f3(r.r0), prev_n = f3(r.r1), d = f3(r.r2);
       float prev_pdf = r.r1.w;
       beta = r.r0.w;
@@ -329,7 +405,7 @@ __global__ void __launch_bounds__(128) k_shade_surface(DevScene S, RenderCtx R, 
 #endif
       if (pdf != pdf) {
         // pdf NaN: the walk breaks BEFORE pushing the vertex (integrator/utils.rs:261-263)
-        atomicAdd(counts + Q_NAN, 1u);
+        n_nan++;
       } else {
         // ---- the vertex exists: its contribution (second loop of pt.rs:481-613)
         if (RPT_MAT_IS_LIGHT(sh.material)) {
@@ -369,8 +445,9 @@ __global__ void __launch_bounds__(128) k_shade_surface(DevScene S, RenderCtx R, 
       }
     }
     // ---- next path queue: one atomic per warp
-    uint32_t k = warp_append(next_counts + Q_PATHS, continues);
+    uint32_t k = chunk_append(next_counts + Q_PATHS, wc_next, continues, mark_next);
     if (continues) out[k] = nr;
+    n_next += continues;
 
     // ---- NEE: warp-uniform loop over the light samples; every iteration compacts the lanes that
     // produced a shadow ray into the shadow queue with one atomic (estimate_direct_illumination_with_loop).
@@ -437,20 +514,26 @@ __global__ void __launch_bounds__(128) k_shade_surface(DevScene S, RenderCtx R, 
             }
           }
         }
-        uint32_t q = warp_append(counts + Q_SHADOW, has);
+        uint32_t q = chunk_append(counts + Q_SHADOW, wc_shadow, has, mark_shadow);
         if (has) {
           sh_a[q] = a;
           sh_b[q] = b4;
           sh_c[q] = c;
         }
+        n_shadow += has;
       }
-      // reference-definition shadow-ray counter (pt.rs:176,252)
-      uint32_t tot = n_sh_ref;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
-      if ((threadIdx.x & 31u) == 0 && tot) atomicAdd(counts + Q_SHADOW_REF, tot);
     }
+    stage ^= 1;
+    idx_cur = idx_next;
+    idx_next = idx_nn;
   }
+  cp_async_wait<0>();
+  if (wc_next.used < QCHUNK) chunk_pad(wc_next, mark_next);
+  if (wc_shadow.used < QCHUNK) chunk_pad(wc_shadow, mark_shadow);
+  flush_count(n_next, next_counts + N_PATHS);
+  flush_count(n_shadow, counts + N_SHADOW);
+  flush_count(n_sh_ref, counts + Q_SHADOW_REF);  // reference-definition shadow-ray counter (pt.rs:176,252)
+  flush_count(n_nan, counts + Q_NAN);
 }
 
 // NEE visibility. Light samples: closest hit, accepted when ANY light-material surface is hit, whose own
@@ -463,8 +546,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
   const uint32_t n = counts[Q_SHADOW];
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float4 a = __ldg(sh_a + i), b = __ldg(sh_b + i);
     uint32_t c = __ldg(sh_c + i);
+    if (c == RPT_NONE) continue;  // chunk padding
+    float4 a = __ldg(sh_a + i), b = __ldg(sh_b + i);
     float3 o = f3(a), d = f3(b);
     float pre = a.w, lambda = b.w;
     uint32_t slot = c & 0x7FFFFFFFu;
@@ -593,7 +677,7 @@ struct RptScene {
   cudaStream_t stream = nullptr;
   // wave buffers (grown on demand, reused across calls)
   WaveBuffers wave{};
-  size_t wave_slots = 0, wave_shadow = 0;
+  size_t wave_slots = 0, wave_shadow = 0, wave_acc = 0;  // capacities: path-queue entries, shadow entries, energy slots
   float4 *film = nullptr;
   size_t film_pixels = 0;
   // launch geometry
@@ -670,34 +754,43 @@ int free_wave(RptScene *S) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   w = WaveBuffers{};
-  S->wave_slots = S->wave_shadow = 0;
+  S->wave_slots = S->wave_shadow = S->wave_acc = 0;
   return 0;
 }
 
-int ensure_wave(RptScene *S, size_t slots, size_t shadow) {
-  if (slots <= S->wave_slots && shadow <= S->wave_shadow) return 0;
+// Queue capacity for `valid` real entries: chunked appends pad at most 31 entries per 256-entry chunk plus one
+// chunk per warp per appending kernel at kernel end (two shade kernels share the next-path and shadow queues).
+size_t queue_cap(size_t valid) { return valid + valid / 8 + ((size_t)4 << 20); }
+
+int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid) {
+  size_t pcap = queue_cap(slots), scap = queue_cap(shadow_valid);
+  if (pcap <= S->wave_slots && scap <= S->wave_shadow && slots <= S->wave_acc) return 0;
   free_wave(S);
   WaveBuffers &w = S->wave;
-  CUDA_TRY(cudaMalloc(&w.paths[0], slots * sizeof(PathRec)));
-  CUDA_TRY(cudaMalloc(&w.paths[1], slots * sizeof(PathRec)));
-  CUDA_TRY(cudaMalloc(&w.hits, slots * sizeof(HitRec)));
-  CUDA_TRY(cudaMalloc(&w.q_miss, slots * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&w.q_diffuse, slots * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&w.q_ggx, slots * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&w.sh_a, std::max<size_t>(shadow, 1) * sizeof(float4)));
-  CUDA_TRY(cudaMalloc(&w.sh_b, std::max<size_t>(shadow, 1) * sizeof(float4)));
-  CUDA_TRY(cudaMalloc(&w.sh_c, std::max<size_t>(shadow, 1) * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.paths[0], pcap * sizeof(PathRec)));
+  CUDA_TRY(cudaMalloc(&w.paths[1], pcap * sizeof(PathRec)));
+  CUDA_TRY(cudaMalloc(&w.hits, pcap * sizeof(HitRec)));
+  CUDA_TRY(cudaMalloc(&w.q_miss, pcap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.q_diffuse, pcap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.q_ggx, pcap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.sh_a, scap * sizeof(float4)));
+  CUDA_TRY(cudaMalloc(&w.sh_b, scap * sizeof(float4)));
+  CUDA_TRY(cudaMalloc(&w.sh_c, scap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&w.acc, slots * sizeof(float)));
   CUDA_TRY(cudaMalloc(&w.counts, (RPT_MAX_BOUNCES + 1) * Q_COUNT * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&w.work, 6 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemset(w.work, 0, 6 * sizeof(unsigned long long)));
-  S->wave_slots = slots;
-  S->wave_shadow = shadow;
+  S->wave_slots = pcap;
+  S->wave_shadow = scap;
+  S->wave_acc = slots;
   return 0;
 }
 
 size_t bytes_per_slot(uint32_t light_samples) {
-  return 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t) + sizeof(float) + (size_t)light_samples * (2 * sizeof(float4) + sizeof(uint32_t));
+  // path queues x2, hit, 3 class lists (all with the 1/8 padding allowance), energy, shadow records
+  size_t per_path = 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t);
+  size_t per_shadow = 2 * sizeof(float4) + sizeof(uint32_t);
+  return per_path + per_path / 8 + sizeof(float) + (size_t)light_samples * (per_shadow + per_shadow / 8);
 }
 
 struct Launcher {
@@ -765,7 +858,7 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   // wave sizing: as many spp per wave as fit the memory budget and the 31-bit slot id
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  size_t held = S->wave_slots * bytes_per_slot(0) + S->wave_shadow * (2 * sizeof(float4) + sizeof(uint32_t));
+  size_t held = S->wave_acc * bytes_per_slot(0) + S->wave_shadow * (2 * sizeof(float4) + sizeof(uint32_t));
   size_t budget = std::min<size_t>((size_t)((free_b + held) * 0.5), (size_t)32 << 30);
   size_t per_slot = bytes_per_slot(P->light_samples);
   size_t max_slots = std::min<size_t>(budget / per_slot, (size_t)1 << 30);
@@ -808,10 +901,10 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       k_shade_miss<<<S->grid[K_SHADE_MISS], 256, 0, S->stream>>>(S->dev, in, w.q_miss, cb, w.acc);
       T.end();
       T.begin(K_SHADE_DIFFUSE);
-      k_shade_surface<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], 128, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
+      k_shade_surface<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
       T.end();
       T.begin(K_SHADE_GGX);
-      k_shade_surface<Q_GGX><<<S->grid[K_SHADE_GGX], 128, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
+      k_shade_surface<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
       T.end();
       if (P->light_samples > 0) {
         T.begin(K_SHADOW);
@@ -830,12 +923,12 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
     C.bounce_rays += R.n_slots;  // the camera vertex (pt.rs:465, integrator/utils.rs:375)
     for (uint32_t b = 0; b < max_bounces; ++b) {
       const uint32_t *c = &h_counts[(size_t)b * Q_COUNT];
-      C.segments += c[Q_PATHS];
-      C.true_rays += c[Q_PATHS] + c[Q_SHADOW];
-      C.env_hits += c[Q_MISS];
-      C.bounce_rays += c[Q_MISS] + c[Q_DIFFUSE] + c[Q_GGX] - c[Q_NAN];
+      C.segments += c[N_PATHS];
+      C.true_rays += c[N_PATHS] + c[N_SHADOW];
+      C.env_hits += c[N_MISS];
+      C.bounce_rays += c[N_MISS] + c[N_DIFFUSE] + c[N_GGX] - c[Q_NAN];
       C.shadow_rays += c[Q_SHADOW_REF];
-      C.shadow_rays_traced += c[Q_SHADOW];
+      C.shadow_rays_traced += c[N_SHADOW];
     }
   }
   size_t ev_last = S->ev_used;
@@ -1164,8 +1257,8 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   }
   S->grid[K_TRACE] = occupancy_grid(k_trace, TRACE_THREADS, S->stack_smem, S->num_sms);
   S->grid[K_SHADE_MISS] = occupancy_grid(k_shade_miss, 256, 0, S->num_sms);
-  S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_surface<Q_DIFFUSE>, 128, 0, S->num_sms);
-  S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_surface<Q_GGX>, 128, 0, S->num_sms);
+  S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_surface<Q_DIFFUSE>, SHADE_THREADS, 0, S->num_sms);
+  S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_surface<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
   S->grid[K_SHADOW] = occupancy_grid(k_shadow, TRACE_THREADS, S->stack_smem, S->num_sms);
   S->grid[K_FILM] = occupancy_grid(k_film, 256, film_smem, S->num_sms);
   *out = S;
