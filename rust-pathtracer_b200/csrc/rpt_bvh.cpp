@@ -127,6 +127,116 @@ struct Builder {
 
 }  // namespace
 
+namespace {
+
+struct SahBuilder {
+  const std::vector<Box> &shapes;
+  std::vector<float> cx, cy, cz;  // centroids
+  BuiltBvh out;
+  static constexpr int kBins = 16;
+
+  explicit SahBuilder(const std::vector<Box> &s) : shapes(s), cx(s.size()), cy(s.size()), cz(s.size()) {
+    for (size_t i = 0; i < s.size(); ++i) {
+      cx[i] = 0.5f * (s[i].mn[0] + s[i].mx[0]);
+      cy[i] = 0.5f * (s[i].mn[1] + s[i].mx[1]);
+      cz[i] = 0.5f * (s[i].mn[2] + s[i].mx[2]);
+    }
+  }
+  float cen(uint32_t i, int axis) const { return axis == 0 ? cx[i] : (axis == 1 ? cy[i] : cz[i]); }
+  static float half_area(const Box &b) {
+    float sx = b.mx[0] - b.mn[0], sy = b.mx[1] - b.mn[1], sz = b.mx[2] - b.mn[2];
+    return sx * sy + sx * sz + sy * sz;
+  }
+
+  int32_t build(uint32_t *idx, size_t n, uint32_t depth) {
+    out.max_depth = std::max(out.max_depth, depth);
+    if (n == 1) return ~(int32_t)idx[0];
+    Box cb = empty_box();
+    for (size_t i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) {
+        float c = cen(idx[i], k);
+        cb.mn[k] = std::fmin(cb.mn[k], c);
+        cb.mx[k] = std::fmax(cb.mx[k], c);
+      }
+    int best_axis = -1, best_split = 0;
+    float best_cost = kInf;
+    for (int axis = 0; axis < 3; ++axis) {
+      float ext = cb.mx[axis] - cb.mn[axis];
+      if (!(ext > 0.0f)) continue;
+      Box bb[kBins];
+      size_t bn[kBins] = {0};
+      for (auto &b : bb) b = empty_box();
+      float scale = (float)kBins / ext;
+      for (size_t i = 0; i < n; ++i) {
+        int b = std::min(kBins - 1, (int)((cen(idx[i], axis) - cb.mn[axis]) * scale));
+        merge(bb[b], shapes[idx[i]]);
+        bn[b]++;
+      }
+      float right_area[kBins];
+      size_t right_n[kBins];
+      Box acc = empty_box();
+      size_t cnt = 0;
+      for (int b = kBins - 1; b > 0; --b) {
+        merge(acc, bb[b]);
+        cnt += bn[b];
+        right_area[b] = half_area(acc);
+        right_n[b] = cnt;
+      }
+      acc = empty_box();
+      cnt = 0;
+      for (int b = 0; b < kBins - 1; ++b) {
+        merge(acc, bb[b]);
+        cnt += bn[b];
+        if (cnt == 0 || right_n[b + 1] == 0) continue;
+        float cost = (float)cnt * half_area(acc) + (float)right_n[b + 1] * right_area[b + 1];
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_axis = axis;
+          best_split = b;
+        }
+      }
+    }
+    size_t mid;
+    if (best_axis < 0) {
+      mid = n / 2;  // all centroids coincide
+    } else {
+      float ext = cb.mx[best_axis] - cb.mn[best_axis], scale = (float)kBins / ext, lo = cb.mn[best_axis];
+      int axis = best_axis, split = best_split;
+      uint32_t *m = std::partition(idx, idx + n, [&](uint32_t i) { return std::min(kBins - 1, (int)((cen(i, axis) - lo) * scale)) <= split; });
+      mid = (size_t)(m - idx);
+      if (mid == 0 || mid == n) mid = n / 2;
+    }
+    int32_t me = (int32_t)out.nodes.size();
+    out.nodes.emplace_back();
+    Box lb = empty_box(), rb = empty_box();
+    for (size_t i = 0; i < mid; ++i) merge(lb, shapes[idx[i]]);
+    for (size_t i = mid; i < n; ++i) merge(rb, shapes[idx[i]]);
+    int32_t l = build(idx, mid, depth + 1);
+    int32_t r = build(idx + mid, n - mid, depth + 1);
+    HostNode &nd = out.nodes[me];
+    for (int k = 0; k < 3; ++k) {
+      nd.lmin[k] = lb.mn[k];
+      nd.lmax[k] = lb.mx[k];
+      nd.rmin[k] = rb.mn[k];
+      nd.rmax[k] = rb.mx[k];
+    }
+    nd.left = l;
+    nd.right = r;
+    return me;
+  }
+};
+
+}  // namespace
+
+BuiltBvh build_bvh_sah(const std::vector<Box> &shapes) {
+  SahBuilder b(shapes);
+  if (shapes.empty()) return std::move(b.out);
+  std::vector<uint32_t> idx(shapes.size());
+  for (size_t i = 0; i < idx.size(); ++i) idx[i] = (uint32_t)i;
+  b.out.root = b.build(idx.data(), idx.size(), 0);
+  return std::move(b.out);
+}
+
 BuiltBvh build_bvh(const std::vector<Box> &shapes) {
   Builder b(shapes);
   if (shapes.empty()) return std::move(b.out);

@@ -33,4 +33,9 @@ struct BuiltBvh {
 
 BuiltBvh build_bvh(const std::vector<Box> &shapes);
 
+// Traversal-quality builder for the DEVICE tree: binned SAH over all three axes (16 bins), one shape per leaf.
+// Which tree the device walks does not change any result (closest hit + tie keys are tree-independent); the
+// reference-order tree above is still built, but only to number the shapes for tie-breaking.
+BuiltBvh build_bvh_sah(const std::vector<Box> &shapes);
+
 }  // namespace rpt

@@ -748,6 +748,25 @@ int occupancy_grid(K kernel, int threads, size_t smem, int num_sms) {
   return per_sm * num_sms;
 }
 
+// One set of wave buffers per device is kept alive across scenes: a host that creates a scene, renders and
+// destroys it every frame (bench.py's e2e leg, the Rust shim) should not pay a multi-GB cudaMalloc each time.
+struct WaveCache {
+  WaveBuffers wave{};
+  size_t slots = 0, shadow = 0, acc = 0;
+  bool valid = false;
+};
+WaveCache g_wave_cache[64];
+
+void release_wave_buffers(WaveBuffers &w) {
+  void *ptrs[] = {w.paths[0], w.paths[1], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.sh_a, w.sh_b, w.sh_c, w.acc, w.counts, w.work};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  w = WaveBuffers{};
+}
+
+// Called at scene destruction: park the buffers in the device's cache (keeping the larger set).
+void park_wave(RptScene *S);
+
 int free_wave(RptScene *S) {
   WaveBuffers &w = S->wave;
   void *ptrs[] = {w.paths[0], w.paths[1], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.sh_a, w.sh_b, w.sh_c, w.acc, w.counts, w.work};
@@ -762,10 +781,42 @@ int free_wave(RptScene *S) {
 // chunk per warp per appending kernel at kernel end (two shade kernels share the next-path and shadow queues).
 size_t queue_cap(size_t valid) { return valid + valid / 8 + ((size_t)4 << 20); }
 
+void park_wave(RptScene *S) {
+  if (S->device < 0 || S->device >= 64 || !S->wave.paths[0]) return;
+  WaveCache &c = g_wave_cache[S->device];
+  if (c.valid && c.slots >= S->wave_slots && c.shadow >= S->wave_shadow && c.acc >= S->wave_acc) {
+    free_wave(S);
+    return;
+  }
+  if (c.valid) release_wave_buffers(c.wave);
+  c.wave = S->wave;
+  c.slots = S->wave_slots;
+  c.shadow = S->wave_shadow;
+  c.acc = S->wave_acc;
+  c.valid = true;
+  S->wave = WaveBuffers{};
+  S->wave_slots = S->wave_shadow = S->wave_acc = 0;
+}
+
 int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid) {
   size_t pcap = queue_cap(slots), scap = queue_cap(shadow_valid);
   if (pcap <= S->wave_slots && scap <= S->wave_shadow && slots <= S->wave_acc) return 0;
   free_wave(S);
+  if (S->device >= 0 && S->device < 64) {
+    WaveCache &c = g_wave_cache[S->device];
+    if (c.valid && pcap <= c.slots && scap <= c.shadow && slots <= c.acc) {
+      S->wave = c.wave;
+      S->wave_slots = c.slots;
+      S->wave_shadow = c.shadow;
+      S->wave_acc = c.acc;
+      c = WaveCache{};
+      return 0;
+    }
+    if (c.valid) {  // too small for this job: release it before allocating a bigger set
+      release_wave_buffers(c.wave);
+      c = WaveCache{};
+    }
+  }
   WaveBuffers &w = S->wave;
   CUDA_TRY(cudaMalloc(&w.paths[0], pcap * sizeof(PathRec)));
   CUDA_TRY(cudaMalloc(&w.paths[1], pcap * sizeof(PathRec)));
@@ -976,7 +1027,7 @@ int rpt_device_count(int *count) {
 int rpt_scene_destroy(RptScene *S) {
   if (!S) return 0;
   cudaSetDevice(S->device);
-  free_wave(S);
+  park_wave(S);
   if (S->film) cudaFree(S->film);
   S->bufs.release();
   for (cudaEvent_t e : S->ev_pool) cudaEventDestroy(e);
@@ -1033,7 +1084,12 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
       }
       boxes[t] = box_of_points(pts, 3);  // MeshTriangleRef::aabb (mesh.rs:57-64)
     }
-    rpt::BuiltBvh bvh = rpt::build_bvh(boxes);
+    rpt::BuiltBvh bvh_ref = rpt::build_bvh(boxes);  // reference candidate order (tie-breaks)
+#ifdef RPT_REFERENCE_TREE
+    rpt::BuiltBvh &bvh = bvh_ref;
+#else
+    rpt::BuiltBvh bvh = rpt::build_bvh_sah(boxes);  // the tree the device walks
+#endif
     minfo[m].tri_base = (uint32_t)(tri_verts.size() / 3);
     minfo[m].box = box_of_points(M.vertices, M.num_vertices);  // Mesh::new bounding box (mesh.rs:271-274)
     minfo[m].has_normals = M.normals != nullptr;
@@ -1046,7 +1102,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
       uint32_t mat = M.face_material ? M.face_material[t] : RPT_MAT_PACK(RPT_MAT_TAG_MATERIAL, 0);
       for (int k = 0; k < 3; ++k) {
         const float *p = M.vertices + 3 * (size_t)M.indices[3 * t + k];
-        uint32_t wbits = k == 0 ? mat : (k == 1 ? bvh.order[t] : 0u);
+        uint32_t wbits = k == 0 ? mat : (k == 1 ? bvh_ref.order[t] : 0u);
         float wf;
         std::memcpy(&wf, &wbits, 4);
         tri_verts.push_back(make_float4(p[0], p[1], p[2], wf));
@@ -1128,7 +1184,11 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
       leaf_box.push_back(ibox[i]);
     }
   }
+#ifdef RPT_REFERENCE_TREE
   rpt::BuiltBvh tlas = rpt::build_bvh(leaf_box);
+#else
+  rpt::BuiltBvh tlas = rpt::build_bvh_sah(leaf_box);
+#endif
   uint32_t needed_blas_depth = 0;
   for (uint32_t i = 0; i < d->num_instances; ++i)
     if (d->instances[i].kind == RPT_AGG_MESH && !flattened[i]) needed_blas_depth = std::max(needed_blas_depth, minfo[d->instances[i].mesh].depth);
