@@ -906,15 +906,25 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   }
   CUDA_TRY(cudaMemsetAsync(S->film, 0, wh * sizeof(float4), S->stream));
 
-  // wave sizing: as many spp per wave as fit the memory budget and the 31-bit slot id
-  size_t free_b = 0, total_b = 0;
-  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  size_t held = S->wave_acc * bytes_per_slot(0) + S->wave_shadow * (2 * sizeof(float4) + sizeof(uint32_t));
-  size_t budget = std::min<size_t>((size_t)((free_b + held) * 0.5), (size_t)32 << 30);
-  size_t per_slot = bytes_per_slot(P->light_samples);
-  size_t max_slots = std::min<size_t>(budget / per_slot, (size_t)1 << 30);
-  uint32_t spp_chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(P->spp ? P->spp : 1, max_slots / wh));
-  if (wh > max_slots) return fail("film does not fit one wave");
+  // wave sizing: as many spp per wave as fit the memory budget and the 30-bit slot id. When the buffers this
+  // scene already holds fit the whole job, skip the (slow) memory query: a steady-state frame loop allocates nothing.
+  uint32_t spp_chunk;
+  size_t want_slots = wh * (size_t)std::max<uint32_t>(P->spp, 1);
+  if (want_slots < ((size_t)1 << 30) && queue_cap(want_slots) <= S->wave_slots && queue_cap(want_slots * P->light_samples) <= S->wave_shadow &&
+      want_slots <= S->wave_acc) {
+    spp_chunk = std::max<uint32_t>(P->spp, 1);
+  } else {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    size_t held = S->wave_acc * bytes_per_slot(0) + S->wave_shadow * (2 * sizeof(float4) + sizeof(uint32_t));
+    if (S->device >= 0 && S->device < 64 && g_wave_cache[S->device].valid)
+      held += g_wave_cache[S->device].acc * bytes_per_slot(0) + g_wave_cache[S->device].shadow * (2 * sizeof(float4) + sizeof(uint32_t));
+    size_t budget = std::min<size_t>((size_t)((free_b + held) * 0.5), (size_t)32 << 30);
+    size_t per_slot = bytes_per_slot(P->light_samples);
+    size_t max_slots = std::min<size_t>(budget / per_slot, (size_t)1 << 30);
+    if (wh > max_slots) return fail("film does not fit one wave");
+    spp_chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(P->spp ? P->spp : 1, max_slots / wh));
+  }
   size_t slots = wh * spp_chunk;
   if (int rc = ensure_wave(S, slots, slots * P->light_samples)) return rc;
 
