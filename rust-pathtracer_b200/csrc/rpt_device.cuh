@@ -82,6 +82,10 @@ struct DevScene {
   // lights / materials / spectra
   uint32_t num_lights;
   const uint32_t *lights;
+  // Every instance whose hits carry a Light material, when all of them are analytic shapes (and there are few):
+  // lets the NEE visibility query run as "closest light, then any occluder in front of it" (k_shadow).
+  uint32_t num_light_geom;  // 0 = two-phase NEE visibility disabled
+  const uint32_t *light_geom;
   const RptMaterial *materials;
   const float *curve_lut;
   const float *cie_lut;
@@ -536,7 +540,7 @@ struct Trav {
     --sp;
     return stack[sp * stride];
   }
-  __device__ __forceinline__ void accept(float t, uint64_t key, uint32_t inst, uint32_t prim) {
+  __device__ __forceinline__ bool accept(float t, uint64_t key, uint32_t inst, uint32_t prim) {
     if (!found || t < closest || key > best_key) {
       closest = t;
       best_key = key;
@@ -544,7 +548,9 @@ struct Trav {
       out.t = t;
       out.inst = inst;
       out.prim = prim;
+      return true;
     }
+    return false;
   }
 
   // "while-while": the inner loop keeps every lane of the warp on the node-test code until each has reached a
@@ -621,10 +627,7 @@ struct Trav {
               hit = sphere_test(I, lo, ld, 0.0f, closest, tmax, t);
             else
               hit = disk_test(I, lo, ld, 0.0f, closest, tmax, t);
-            if (hit) {
-              accept(t, tie_key(kind == RPT_AGG_SPHERE, inst_order, 0), hit_inst, 0);
-              if (ANY_HIT) return;
-            }
+            if (hit && accept(t, tie_key(kind == RPT_AGG_SPHERE, inst_order, 0), hit_inst, 0) && ANY_HIT) return;
           }
         }
       }
@@ -633,10 +636,9 @@ struct Trav {
         const float4 *tv = S.tri_verts + 3 * (size_t)tri;
         float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
         float t, b0, b1, b2;
-        if (tri_test_pre(f3(v0), f3(v1), f3(v2), ro, tr, 0.0f, closest, t, b0, b1, b2)) {
-          accept(t, tie_key(false, inst_order, __float_as_uint(v1.w)), hit_inst, tri_local);
-          if (ANY_HIT) return;
-        }
+        if (tri_test_pre(f3(v0), f3(v1), f3(v2), ro, tr, 0.0f, closest, t, b0, b1, b2) &&
+            accept(t, tie_key(false, inst_order, __float_as_uint(v1.w)), hit_inst, tri_local) && ANY_HIT)
+          return;
       }
       cur = have_next ? next : pop(stack, stride);
       if (cur == RPT_DONE) return;

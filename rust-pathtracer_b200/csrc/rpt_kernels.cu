@@ -555,20 +555,66 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
     TraceHit th;
     if (c & 0x80000000u) {
       if (!trace_ray<true>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) atomicAdd(acc + slot, pre);
-    } else {
-      if (trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) {
-        SurfaceHit sh;
-        reconstruct_hit(S, o, d, th, sh);
-        if (RPT_MAT_IS_LIGHT(sh.material)) {
-          Frame lf = frame_from_normal(sh.n);
-          float3 lwi = to_local(lf, -d);
-          float le = material_emission(S, S.materials[RPT_MAT_INDEX(sh.material)], lambda, lwi);
-          float v = pre * fabsf(lwi.z) * le;
-#ifdef RPT_DEBUG
-          if (slot == RPT_DEBUG_SLOT) printf("[shadow] hit inst=%u prim=%u t=%.7g le=%.7g lwi.z=%.7g pre=%.7g -> %.7g\n", th.inst, th.prim, th.t, le, lwi.z, pre, v);
-#endif
-          if (v != 0.0f) atomicAdd(acc + slot, v);
+      continue;
+    }
+    bool lit;
+    if (S.num_light_geom) {
+      // Two-phase form of "the closest hit must be a light" (exact, including the reference's tie rule):
+      // (A) the closest hit among the few light-material shapes, (B) ANY hit of the scene in front of it.
+      float tl = RPT_INF;
+      uint64_t key_l = 0;
+      bool found_l = false;
+      uint32_t inst_l = RPT_NONE;
+      for (uint32_t k = 0; k < S.num_light_geom; ++k) {
+        uint32_t li = __ldg(S.light_geom + k);
+        const DevInstance &I = S.instances[li];
+        uint32_t flags = I.flags;
+        float3 lo = o, ld = d;
+        if (flags & DI_HAS_TRANSFORM) {
+          lo = xform_point(I.rev, o);
+          ld = xform_vec(I.rev, d);
         }
+        uint32_t kind = flags & DI_KIND_MASK;
+        float t;
+        bool hit = kind == RPT_AGG_RECT ? rect_test(I, lo, ld, 0.0f, tl, RPT_INF, t)
+                                        : (kind == RPT_AGG_SPHERE ? sphere_test(I, lo, ld, 0.0f, tl, RPT_INF, t) : disk_test(I, lo, ld, 0.0f, tl, RPT_INF, t));
+        tw.insts++;
+        if (hit) {
+          uint64_t key = tie_key(kind == RPT_AGG_SPHERE, I.order, 0);
+          if (!found_l || t < tl || key > key_l) {
+            tl = t;
+            key_l = key;
+            found_l = true;
+            inst_l = li;
+          }
+        }
+      }
+      if (!found_l) continue;  // no light along the ray: nothing to add
+      Trav tv;
+      tv.init(S, o, d, RPT_INF);
+      tv.closest = tl;  // only geometry that beats the light (closer, or equal t with a winning tie key) is accepted
+      tv.best_key = key_l;
+      tv.found = true;
+      tv.template run<true>(S, s_stack + threadIdx.x, TRACE_THREADS, tw);
+      lit = tv.best_key == key_l && tv.closest == tl;
+      th.t = tl;
+      th.inst = inst_l;
+      th.prim = 0;
+    } else {
+      lit = trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+    }
+    if (lit) {
+      SurfaceHit sh;
+      reconstruct_hit(S, o, d, th, sh);
+      if (RPT_MAT_IS_LIGHT(sh.material)) {
+        Frame lf = frame_from_normal(sh.n);
+        float3 lwi = to_local(lf, -d);
+        float le = material_emission(S, S.materials[RPT_MAT_INDEX(sh.material)], lambda, lwi);
+        float v = pre * fabsf(lwi.z) * le;
+#ifdef RPT_DEBUG
+        if (slot == RPT_DEBUG_SLOT) printf("[shadow] hit inst=%u prim=%u t=%.7g le=%.7g lwi.z=%.7g pre=%.7g -> %.7g\n", th.inst, th.prim, th.t, le, lwi.z, pre, v);
+#endif
+        if (v != 0.0f) atomicAdd(acc + slot, v);
       }
     }
   }
@@ -1244,6 +1290,23 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
       return bail(fail("mesh lights are unimplemented in the reference (src/geometry/mesh.rs:362-386 todo!())"));
   }
 
+  // light-material geometry for the two-phase NEE visibility query (k_shadow)
+  std::vector<uint32_t> light_geom;
+  bool light_geom_ok = true;
+  for (uint32_t i = 0; i < d->num_instances; ++i) {
+    const RptInstance &I = d->instances[i];
+    bool override_light = I.material != RPT_MAT_NONE && RPT_MAT_IS_LIGHT(I.material);
+    if (I.kind == RPT_AGG_MESH) {
+      if (override_light) light_geom_ok = false;
+      if (I.material == RPT_MAT_NONE && d->meshes[I.mesh].face_material)
+        for (uint32_t t = 0; t < d->meshes[I.mesh].num_faces; ++t)
+          if (RPT_MAT_IS_LIGHT(d->meshes[I.mesh].face_material[t])) light_geom_ok = false;
+    } else if (override_light) {
+      light_geom.push_back(i);
+    }
+  }
+  if (!light_geom_ok || light_geom.size() > 8) light_geom.clear();
+
   DevScene &D = S->dev;
   DeviceBuffers &B = S->bufs;
   int rc = 0;
@@ -1253,6 +1316,8 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   rc |= B.upload(tri_verts.data(), tri_verts.size(), &D.tri_verts);
   rc |= B.upload(tri_normals.data(), tri_normals.size(), &D.tri_normals);
   rc |= B.upload(d->lights, d->num_lights, &D.lights);
+  rc |= B.upload(light_geom.data(), light_geom.size(), &D.light_geom);
+  D.num_light_geom = (uint32_t)light_geom.size();
   rc |= B.upload(d->materials, d->num_materials, &D.materials);
   rc |= B.upload(d->curve_lut, (size_t)d->num_curves * d->num_lambda, &D.curve_lut);
   rc |= B.upload(d->cie_lut, 3 * (size_t)d->num_lambda, &D.cie_lut);
