@@ -176,6 +176,20 @@ def test_public_api_render(pkg):
     os_.close()
 
 
+def test_tma_tile_variant(monkeypatch):
+    """k_trace with TMA-staged queue tiles (cp.async.bulk + mbarrier, RPT_TMA_TILES=1) is bit-identical to the default."""
+    world, st, flat = parity.load_scene("cornell", 160, 90, 4)
+    base = parity.cuda_scene(flat)
+    f0, c0 = base.render_pt(st.params(seed=21))
+    monkeypatch.setenv("RPT_TMA_TILES", "1")
+    tma = parity.cuda_scene(flat)
+    f1, c1 = tma.render_pt(st.params(seed=21))
+    assert c0.segments == c1.segments and c0.shadow_rays == c1.shadow_rays
+    assert np.allclose(f0, f1, rtol=1e-6, atol=1e-9)  # only the order of the energy atomics may differ
+    base.close()
+    tma.close()
+
+
 def test_kernel_times_and_stats(scenes):
     st, cs, _ = scenes("cornell", 96, 54, 8)
     cs.render_pt(st.params(seed=1))
