@@ -105,6 +105,7 @@ struct DevScene {
   uint32_t imap_rows, imap_cols, imap_marginal_n;
   const float *imap_row_pdf, *imap_row_cdf, *imap_m_pdf, *imap_m_cdf;
   float imap_marginal_integral;
+  float3 world_center; // centre of the scene bounds (ray binning only)
   float p_env;         // effective env sampling probability (1 when there are no lights)
   float world_radius;  // World.radius (world/mod.rs:69-72); informational
 };
