@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RPT_ABI_VERSION 4u
+#define RPT_ABI_VERSION 5u
 
 /* ---- MaterialId (reference src/materials/mod.rs:22-27) --------------------------
  * Packed as (tag << 16) | table_index; RPT_MAT_NONE = "no override / no id". */
@@ -261,6 +261,29 @@ int rpt_film_scale(RptScene *scene, void *film_dev, uint64_t n_float4, float sca
 
 /* Timing of the last render: fills up to cap entries, returns count in *n. */
 int rpt_last_kernel_times(RptScene *scene, RptKernelTime *out, uint32_t cap, uint32_t *n);
+
+/* ---- output_film: the step right after the hot path -------------------------------------
+ * reference src/renderer/mod.rs:24-80 (output_film) -> src/tonemap/{clamp,reinhard0,reinhard1}.rs (initialize + map)
+ * -> src/tonemap/mod.rs:207-338 (write_to_files): linear RGB in the chosen primaries for the EXR, tonemapped +
+ * OETF-encoded 8-bit RGBA for the PNG. File encoding itself stays on the host. */
+enum RptTonemapper { RPT_TONEMAP_CLAMP = 0, RPT_TONEMAP_REINHARD0 = 1, RPT_TONEMAP_REINHARD1 = 2 };
+enum RptColorSpace { RPT_COLORSPACE_SRGB = 0, RPT_COLORSPACE_REC709 = 1, RPT_COLORSPACE_REC2020 = 2 };
+typedef struct RptOutputSettings {
+  uint32_t tonemapper;     /* RptTonemapper (parsing/tonemap.rs:9-31) */
+  uint32_t luminance_only; /* false selects the per-channel x3 variants of Reinhard0/1 */
+  float exposure;          /* Clamp: 2^exposure multiplier (clamp.rs:83) */
+  float key_value;         /* Reinhard0/1 */
+  float white_point;       /* Reinhard1 */
+  uint32_t colorspace;     /* RptColorSpace (parsing/config.rs:33-43) */
+  float factor;            /* output_film's factor x premultiply (renderer/mod.rs:25) */
+} RptOutputSettings;
+
+/* Tonemaps the film. film_xyzw: host film (w*h*4 floats) or NULL to use the device-resident film of the scene's
+ * last render (no re-upload). rgb_linear: optional host out, w*h*3 floats = M(factor * XYZ) (the EXR payload).
+ * rgba8: host out, w*h*4 bytes = ceil(255 * OETF(M(map(XYZ)))) clamped, alpha 255 (the PNG payload).
+ * l_w: optional out, the 4 lanes of the tonemapper's log-average (lane 0..2 = X,Y,Z for x3 variants; Y only else). */
+int rpt_output_film(RptScene *scene, const float *film_xyzw, uint32_t width, uint32_t height, const RptOutputSettings *settings,
+                    float *rgb_linear, uint8_t *rgba8, float *l_w);
 
 /* BVH statistics for roofline accounting: bytes of nodes / primitives. */
 typedef struct RptSceneStats {

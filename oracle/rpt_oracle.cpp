@@ -1543,6 +1543,110 @@ int rpto_trace_rays(RptScene *S, uint32_t n, const float *o, const float *d, con
   return 0;
 }
 
+// ---- output_film (renderer/mod.rs:24-80): Tonemapper::initialize + map (tonemap/{clamp,reinhard0,reinhard1}.rs),
+// XYZ -> RGB (tonemap/mod.rs:24-40,116-140), OETF (:147-205), byte encoding (:314-331). Sequential like the reference.
+namespace {
+const float XYZ_TO_REC709[9] = {3.24096994f, -1.53738318f, -0.49861076f, -0.96924364f, 1.8759675f, 0.04155506f, 0.05563008f, -0.20397696f, 1.05697151f};
+const float XYZ_TO_REC2020[9] = {1.4628067f, -0.1840623f, -0.2743606f, -0.5217933f, 1.4472381f, 0.0677227f, 0.0349342f, -0.0968930f, 1.2884099f};
+const float MAUVE_XYZ[3] = {0.5199467f, 51.48687f, 1.0180528f};  // src/lib.rs:46
+inline float oetf(float v, uint32_t cs) {
+  if (cs == RPT_COLORSPACE_SRGB) return v < 0.0031308f ? (323.0f / 25.0f) * v : (211.0f / 200.0f) * std::pow(v, 5.0f / 12.0f) - (11.0f / 200.0f);
+  return v < 0.01805397f ? 4.5f * v : 1.0992968f * std::pow(v, 0.45f) - 0.09929682f;
+}
+inline bool finite3(const float *c) { return std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && std::isfinite(c[3]); }
+}  // namespace
+
+int rpto_output_film(RptScene *, const float *film, uint32_t W, uint32_t H, const RptOutputSettings *O, float *rgb_linear, uint8_t *rgba8, float *l_w_out) {
+  if (!film || !O || !rgba8) return fail("null argument");
+  if (!(O->factor > 0.0f)) return fail("factor must be > 0 (renderer/mod.rs:26)");
+  const size_t n = (size_t)W * H;
+  const float *M = O->colorspace == RPT_COLORSPACE_REC2020 ? XYZ_TO_REC2020 : XYZ_TO_REC709;
+  // ---- initialize
+  float lw[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+  const bool x3 = !O->luminance_only && O->tonemapper != RPT_TONEMAP_CLAMP;
+  if (O->tonemapper != RPT_TONEMAP_CLAMP) {
+    double sum_log = 0.0;
+    float sum_log4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (size_t i = 0; i < n; ++i) {
+      const float *c = film + 4 * i;
+      float lum = c[1];
+      if (std::isnan(lum)) continue;
+      if (x3) {
+        for (int k = 0; k < 4; ++k) sum_log4[k] += std::log(0.001f + c[k]);
+      } else if (O->tonemapper == RPT_TONEMAP_REINHARD0) {
+        sum_log += std::log(0.001 + (double)lum);  // reinhard0.rs:48 (f64 DELTA)
+      } else {
+        sum_log += std::log((double)(0.001f + lum));  // reinhard1.rs:47 (f32 add, then f64)
+      }
+    }
+    if (x3)
+      for (int k = 0; k < 4; ++k) lw[k] = std::exp(sum_log4[k] / (float)n) / O->factor;
+    else
+      lw[0] = lw[1] = lw[2] = lw[3] = (float)std::exp(sum_log / (double)n) / O->factor;
+  }
+  if (l_w_out) std::memcpy(l_w_out, lw, sizeof(lw));
+  // ---- per pixel
+  for (size_t i = 0; i < n; ++i) {
+    const float *c = film + 4 * i;
+    if (rgb_linear) {  // EXR payload: M * (factor * XYZ) (tonemap/mod.rs:225-247)
+      float x = O->factor * c[0], y = O->factor * c[1], z = O->factor * c[2];
+      for (int r = 0; r < 3; ++r) rgb_linear[3 * i + r] = M[3 * r] * x + M[3 * r + 1] * y + M[3 * r + 2] * z;
+    }
+    float m[3];
+    if (O->tonemapper == RPT_TONEMAP_CLAMP) {  // clamp.rs:76-101
+      float v[4] = {c[0] * O->factor, c[1] * O->factor, c[2] * O->factor, c[3] * O->factor};
+      if (!finite3(v)) { v[0] = MAUVE_XYZ[0]; v[1] = MAUVE_XYZ[1]; v[2] = MAUVE_XYZ[2]; }
+      float em = std::pow(2.0f, O->exposure);
+      if (O->luminance_only) {
+        float lum = v[1];
+        float new_lum = clampf(lum * em, 0.0f, 1.0f);
+        float sf = new_lum / lum;
+        for (int k = 0; k < 3; ++k) m[k] = sf * v[k];
+      } else {
+        for (int k = 0; k < 3; ++k) m[k] = std::fmax(std::fmin(v[k] * em, 1.0f), 0.0f);
+      }
+    } else if (!x3) {  // reinhard0.rs:96-113 / reinhard1.rs:88-107
+      float lum = c[1];
+      float l = O->key_value * lum / lw[1];
+      float sf;
+      if (O->tonemapper == RPT_TONEMAP_REINHARD0) {
+        sf = l / (1.0f + l);
+      } else {
+        float mul = 1.0f / (O->white_point * O->white_point);
+        sf = l * (mul * l + 1.0f) / (1.0f + l);
+      }
+      float v[3] = {c[0], c[1], c[2]};
+      if (!finite3(c)) { v[0] = MAUVE_XYZ[0]; v[1] = MAUVE_XYZ[1]; v[2] = MAUVE_XYZ[2]; }
+      for (int k = 0; k < 3; ++k) m[k] = sf * v[k];
+    } else {  // reinhard0.rs:196-213 / reinhard1.rs:198-232 (per channel)
+      bool bad = false;
+      float v[3] = {c[0], c[1], c[2]};
+      if (O->tonemapper == RPT_TONEMAP_REINHARD0 && !finite3(c)) { v[0] = MAUVE_XYZ[0]; v[1] = MAUVE_XYZ[1]; v[2] = MAUVE_XYZ[2]; }
+      for (int k = 0; k < 3; ++k) {
+        float l = O->key_value * c[k] / lw[k];
+        float sf;
+        if (O->tonemapper == RPT_TONEMAP_REINHARD0) {
+          sf = l / (1.0f + l);
+        } else {
+          float mul = 1.0f / std::pow(O->white_point, 2.0f);
+          sf = l * (mul * l + 1.0f) / (1.0f + l);
+        }
+        m[k] = sf * v[k];
+        if (!std::isfinite(m[k])) bad = true;
+      }
+      if (O->tonemapper == RPT_TONEMAP_REINHARD1 && bad) { m[0] = MAUVE_XYZ[0]; m[1] = MAUVE_XYZ[1]; m[2] = MAUVE_XYZ[2]; }
+    }
+    for (int r = 0; r < 3; ++r) {
+      float lin = M[3 * r] * m[0] + M[3 * r + 1] * m[1] + M[3 * r + 2] * m[2];
+      float e = std::ceil(oetf(lin, O->colorspace) * 255.0f);
+      e = e < 0.0f ? 0.0f : (e > 255.0f ? 255.0f : e);  // NaN stays NaN -> `as u8` = 0
+      rgba8[4 * i + r] = std::isnan(e) ? 0 : (uint8_t)e;
+    }
+    rgba8[4 * i + 3] = 255;
+  }
+  return 0;
+}
+
 // ---- unit hooks for the known-answer tests (tests/test_oracle_*.py) ----------------------------------------
 // ggx_glass(roughness) of the reference's tests: eta = cauchy(1.5, 10000), eta_o = 1, kappa = 0 (ggx.rs:630-635)
 void rpto_ggx_bsdf(float alpha, float eta_inner, float eta_outer, float kappa, int metallic, const float *wi, const float *wo, float *f, float *pdf) {

@@ -788,6 +788,137 @@ __global__ void k_scale(float4 *film, uint64_t n, float s) {
   }
 }
 
+// ---- output_film on the device: Tonemapper::initialize = one reduction over the film,
+// Tonemapper::map + XYZ->RGB + OETF + byte encoding = one map kernel (renderer/mod.rs:24-80, tonemap/*.rs).
+__constant__ float c_xyz_to_rec709[9] = {3.24096994f, -1.53738318f, -0.49861076f, -0.96924364f, 1.8759675f, 0.04155506f, 0.05563008f, -0.20397696f, 1.05697151f};
+__constant__ float c_xyz_to_rec2020[9] = {1.4628067f, -0.1840623f, -0.2743606f, -0.5217933f, 1.4472381f, 0.0677227f, 0.0349342f, -0.0968930f, 1.2884099f};
+
+// sums[0..3] += sum over non-NaN-luminance pixels of ln(0.001 + channel) (double accumulation: the reference sums
+// sequentially in f64 (luminance variants) or f32 (x3 variants); a parallel double sum is within 1e-6 of either)
+__global__ void __launch_bounds__(256) k_out_reduce(const float4 *__restrict__ film, uint64_t n, int mode /*0 y f64-delta, 1 y f32-delta, 2 x3*/,
+                                                    double *__restrict__ sums) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float4 c = film[i];
+    if (c.y != c.y) continue;
+    if (mode == 2) {
+      acc[0] += (double)logf(0.001f + c.x);
+      acc[1] += (double)logf(0.001f + c.y);
+      acc[2] += (double)logf(0.001f + c.z);
+      acc[3] += (double)logf(0.001f + c.w);
+    } else if (mode == 0) {
+      acc[1] += log(0.001 + (double)c.y);
+    } else {
+      acc[1] += log((double)(0.001f + c.y));
+    }
+  }
+  __shared__ double s_red[4][8];
+  for (int k = 0; k < 4; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += s_red[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, v);
+  }
+}
+
+// The x3 tonemappers accumulate ln(0.001 + XYZW) in f32, pixel by pixel (reinhard0.rs:154, reinhard1.rs:163): at
+// 2 M pixels that sum carries an order-dependent rounding error of a few 1e-4 relative, which moves l_w and with it
+// every output byte. To return the reference's numbers the device reproduces the ORDER: logs in parallel, then one
+// strictly sequential f32 chain per channel (4 lanes, ~4 cycles per add: ~4 ms for a 1080p film, once per frame).
+__global__ void __launch_bounds__(256) k_out_log(const float4 *__restrict__ film, uint64_t n, float4 *__restrict__ logs) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float4 c = film[i];
+    logs[i] = (c.y != c.y) ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(logf(0.001f + c.x), logf(0.001f + c.y), logf(0.001f + c.z), logf(0.001f + c.w));
+  }
+}
+__global__ void k_out_seqsum(const float *__restrict__ logs, uint64_t n, double *__restrict__ sums) {
+  if (threadIdx.x < 4) {
+    float s = 0.0f;
+    const float *p = logs + threadIdx.x;
+#pragma unroll 8
+    for (uint64_t i = 0; i < n; ++i) s = __fadd_rn(s, p[4 * i]);
+    sums[threadIdx.x] = (double)s;
+  }
+}
+
+__device__ __forceinline__ float oetf_dev(float v, uint32_t cs) {
+  if (cs == RPT_COLORSPACE_SRGB) return v < 0.0031308f ? (323.0f / 25.0f) * v : (211.0f / 200.0f) * powf(v, 5.0f / 12.0f) - (11.0f / 200.0f);
+  return v < 0.01805397f ? 4.5f * v : 1.0992968f * powf(v, 0.45f) - 0.09929682f;
+}
+
+__global__ void __launch_bounds__(256) k_out_map(const float4 *__restrict__ film, uint64_t n, RptOutputSettings O, float4 lw,
+                                                 float *__restrict__ rgb_linear, uchar4 *__restrict__ rgba8) {
+  const float *M = O.colorspace == RPT_COLORSPACE_REC2020 ? c_xyz_to_rec2020 : c_xyz_to_rec709;
+  const float3 mauve = f3(0.5199467f, 51.48687f, 1.0180528f);  // src/lib.rs:46
+  const bool x3 = !O.luminance_only && O.tonemapper != RPT_TONEMAP_CLAMP;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float4 c = film[i];
+    if (rgb_linear) {  // EXR payload (tonemap/mod.rs:225-247)
+      float x = O.factor * c.x, y = O.factor * c.y, z = O.factor * c.z;
+      for (int r = 0; r < 3; ++r) rgb_linear[3 * i + r] = M[3 * r] * x + M[3 * r + 1] * y + M[3 * r + 2] * z;
+    }
+    bool fin = isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w);
+    float3 m;
+    if (O.tonemapper == RPT_TONEMAP_CLAMP) {  // clamp.rs:76-101
+      float4 v = make_float4(c.x * O.factor, c.y * O.factor, c.z * O.factor, c.w * O.factor);
+      float3 col = f3(v);
+      if (!(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w))) col = mauve;
+      float em = powf(2.0f, O.exposure);
+      if (O.luminance_only) {
+        float sf = clampf(col.y * em, 0.0f, 1.0f) / col.y;
+        m = sf * col;
+      } else {
+        m = f3(fmaxf(fminf(col.x * em, 1.0f), 0.0f), fmaxf(fminf(col.y * em, 1.0f), 0.0f), fmaxf(fminf(col.z * em, 1.0f), 0.0f));
+      }
+    } else if (!x3) {  // reinhard0.rs:96-113 / reinhard1.rs:88-107
+      float l = O.key_value * c.y / lw.y;
+      float sf;
+      if (O.tonemapper == RPT_TONEMAP_REINHARD0) {
+        sf = l / (1.0f + l);
+      } else {
+        float mul = 1.0f / (O.white_point * O.white_point);
+        sf = l * (mul * l + 1.0f) / (1.0f + l);
+      }
+      float3 col = fin ? f3(c) : mauve;
+      m = sf * col;
+    } else {  // per channel (reinhard0.rs:196-213 / reinhard1.rs:198-232)
+      float3 col = (O.tonemapper == RPT_TONEMAP_REINHARD0 && !fin) ? mauve : f3(c);
+      float cc[3] = {c.x, c.y, c.z}, lwv[3] = {lw.x, lw.y, lw.z}, cv[3] = {col.x, col.y, col.z}, mm[3];
+      bool bad = false;
+      for (int k = 0; k < 3; ++k) {
+        float l = O.key_value * cc[k] / lwv[k];
+        float sf;
+        if (O.tonemapper == RPT_TONEMAP_REINHARD0) {
+          sf = l / (1.0f + l);
+        } else {
+          float mul = 1.0f / powf(O.white_point, 2.0f);
+          sf = l * (mul * l + 1.0f) / (1.0f + l);
+        }
+        mm[k] = sf * cv[k];
+        bad |= !isfinite(mm[k]);
+      }
+      m = f3(mm[0], mm[1], mm[2]);
+      if (O.tonemapper == RPT_TONEMAP_REINHARD1 && bad) m = mauve;
+    }
+    unsigned char b[3];
+    for (int r = 0; r < 3; ++r) {
+      float lin = M[3 * r] * m.x + M[3 * r + 1] * m.y + M[3 * r + 2] * m.z;
+      float e = ceilf(oetf_dev(lin, O.colorspace) * 255.0f);
+      e = e < 0.0f ? 0.0f : (e > 255.0f ? 255.0f : e);
+      b[r] = (e != e) ? 0 : (unsigned char)e;  // NaN -> 0 like Rust's `as u8`
+    }
+    rgba8[i] = make_uchar4(b[0], b[1], b[2], 255);
+  }
+}
+
 // generic closest-hit query of host-provided rays (rpt_trace_rays)
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32_t n, const float *__restrict__ o, const float *__restrict__ d,
                                                               const float *__restrict__ tmax, HitRec *__restrict__ hits) {
@@ -1616,6 +1747,68 @@ int rpt_trace_rays(RptScene *S, uint32_t n, const float *origins, const float *d
     prim[i] = h[i].prim;
     t[i] = h[i].t;
   }
+  return 0;
+}
+
+int rpt_output_film(RptScene *S, const float *film_xyzw, uint32_t width, uint32_t height, const RptOutputSettings *O, float *rgb_linear,
+                    uint8_t *rgba8, float *l_w) {
+  if (!S || !O || !rgba8) return fail("null argument");
+  if (!(O->factor > 0.0f)) return fail("factor must be > 0 (renderer/mod.rs:26)");
+  if (O->tonemapper > RPT_TONEMAP_REINHARD1 || O->colorspace > RPT_COLORSPACE_REC2020) return fail("unknown tonemapper / colour space");
+  CUDA_TRY(cudaSetDevice(S->device));
+  const uint64_t n = (uint64_t)width * height;
+  if (n == 0) return fail("empty film");
+  float4 *film = nullptr, *owned = nullptr;
+  if (film_xyzw) {
+    CUDA_TRY(cudaMalloc(&owned, n * sizeof(float4)));
+    film = owned;
+    CUDA_TRY(cudaMemcpyAsync(film, film_xyzw, n * sizeof(float4), cudaMemcpyHostToDevice, S->stream));
+  } else {
+    if (!S->film || S->film_pixels != n) return fail("no device-resident film of that size: render first or pass film_xyzw");
+    film = S->film;
+  }
+  double *d_sums = nullptr;
+  float *d_rgb = nullptr;
+  uchar4 *d_rgba = nullptr;
+  CUDA_TRY(cudaMalloc(&d_sums, 4 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&d_rgba, n * sizeof(uchar4)));
+  if (rgb_linear) CUDA_TRY(cudaMalloc(&d_rgb, 3 * n * sizeof(float)));
+  CUDA_TRY(cudaMemsetAsync(d_sums, 0, 4 * sizeof(double), S->stream));
+  float4 lw = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+  const bool x3 = !O->luminance_only && O->tonemapper != RPT_TONEMAP_CLAMP;
+  if (O->tonemapper != RPT_TONEMAP_CLAMP) {
+    float4 *d_logs = nullptr;
+    if (x3) {
+      CUDA_TRY(cudaMalloc(&d_logs, n * sizeof(float4)));
+      k_out_log<<<S->num_sms * 4, 256, 0, S->stream>>>(film, n, d_logs);
+      k_out_seqsum<<<1, 32, 0, S->stream>>>(reinterpret_cast<const float *>(d_logs), n, d_sums);
+    } else {
+      k_out_reduce<<<S->num_sms * 4, 256, 0, S->stream>>>(film, n, O->tonemapper == RPT_TONEMAP_REINHARD0 ? 0 : 1, d_sums);
+    }
+    double h[4];
+    CUDA_TRY(cudaMemcpyAsync(h, d_sums, sizeof(h), cudaMemcpyDeviceToHost, S->stream));
+    CUDA_TRY(cudaStreamSynchronize(S->stream));
+    if (d_logs) cudaFree(d_logs);
+    if (x3) {
+      lw = make_float4(std::exp((float)h[0] / (float)n) / O->factor, std::exp((float)h[1] / (float)n) / O->factor,
+                       std::exp((float)h[2] / (float)n) / O->factor, std::exp((float)h[3] / (float)n) / O->factor);
+    } else {
+      float v = (float)std::exp(h[1] / (double)n) / O->factor;
+      lw = make_float4(v, v, v, v);
+    }
+  }
+  k_out_map<<<S->num_sms * 4, 256, 0, S->stream>>>(film, n, *O, lw, d_rgb, d_rgba);
+  CUDA_TRY(cudaMemcpyAsync(rgba8, d_rgba, n * sizeof(uchar4), cudaMemcpyDeviceToHost, S->stream));
+  if (rgb_linear) CUDA_TRY(cudaMemcpyAsync(rgb_linear, d_rgb, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, S->stream));
+  CUDA_TRY(cudaStreamSynchronize(S->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (l_w) {
+    l_w[0] = lw.x; l_w[1] = lw.y; l_w[2] = lw.z; l_w[3] = lw.w;
+  }
+  cudaFree(d_sums);
+  cudaFree(d_rgba);
+  if (d_rgb) cudaFree(d_rgb);
+  if (owned) cudaFree(owned);
   return 0;
 }
 

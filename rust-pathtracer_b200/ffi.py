@@ -17,7 +17,7 @@ from . import curves as C
 from . import world as W
 
 F32 = np.float32
-ABI_VERSION = 4
+ABI_VERSION = 5
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "librpt_b200.so")
@@ -113,6 +113,13 @@ class RptCounters(ct.Structure):
         return {k: (float(getattr(self, k)) if k == "device_ms" else int(getattr(self, k))) for k, _ in self._fields_}
 
 
+class RptOutputSettings(ct.Structure):
+    _fields_ = [
+        ("tonemapper", c_u32), ("luminance_only", c_u32), ("exposure", c_f), ("key_value", c_f), ("white_point", c_f),
+        ("colorspace", c_u32), ("factor", c_f),
+    ]
+
+
 class RptKernelTime(ct.Structure):
     _fields_ = [("name", ct.c_char_p), ("launches", c_u32), ("ms", c_f)]
 
@@ -128,7 +135,7 @@ class RptSceneStats(ct.Structure):
 RPT_SYMBOLS = [
     "rpt_last_error", "rpt_abi_version", "rpt_device_count", "rpt_scene_create", "rpt_scene_destroy",
     "rpt_render_pt", "rpt_render_pt_device", "rpt_trace_primary", "rpt_trace_rays", "rpt_film_scale",
-    "rpt_last_kernel_times", "rpt_scene_stats",
+    "rpt_last_kernel_times", "rpt_scene_stats", "rpt_output_film",
 ]
 
 
@@ -181,6 +188,8 @@ def load_library(path: Optional[str] = None) -> ct.CDLL:
     lib.rpt_last_kernel_times.restype = ct.c_int
     lib.rpt_scene_stats.argtypes = [ct.c_void_p, ct.POINTER(RptSceneStats)]
     lib.rpt_scene_stats.restype = ct.c_int
+    lib.rpt_output_film.argtypes = [ct.c_void_p, ct.c_void_p, c_u32, c_u32, ct.POINTER(RptOutputSettings), ct.c_void_p, ct.c_void_p, ct.c_void_p]
+    lib.rpt_output_film.restype = ct.c_int
     if lib.rpt_abi_version() != ABI_VERSION:
         raise RptError(f"ABI mismatch: library {lib.rpt_abi_version()} vs binding {ABI_VERSION}; rebuild")
     if path is None:
@@ -380,6 +389,23 @@ class Scene:
         if rc != 0:
             raise RptError(self._err())
         return inst, prim, t
+
+    def output_film(self, settings: "RptOutputSettings", film: Optional[np.ndarray], width: int, height: int):
+        """-> (rgb_linear (H, W, 3) f32, rgba8 (H, W, 4) u8, l_w (4,) f32). film=None uses the device film of the last render."""
+        rgb = np.zeros((height, width, 3), dtype=F32)
+        rgba = np.zeros((height, width, 4), dtype=np.uint8)
+        lw = np.zeros(4, dtype=F32)
+        fp = None
+        if film is not None:
+            film = np.ascontiguousarray(film, dtype=F32)
+            fp = film.ctypes.data_as(ct.c_void_p)
+        vp = lambda a: a.ctypes.data_as(ct.c_void_p)
+        fn = self._fn("output_film")
+        fn.argtypes = [ct.c_void_p, ct.c_void_p, c_u32, c_u32, ct.POINTER(RptOutputSettings), ct.c_void_p, ct.c_void_p, ct.c_void_p]
+        fn.restype = ct.c_int
+        if fn(self.handle, fp, width, height, ct.byref(settings), vp(rgb), vp(rgba), vp(lw)) != 0:
+            raise RptError(self._err())
+        return rgb, rgba, lw
 
     def kernel_times(self) -> List[dict]:
         buf = (RptKernelTime * 32)()

@@ -79,6 +79,27 @@ class PTSettings:
         return p
 
 
+TONEMAPPERS = {"Clamp": 0, "Reinhard0": 1, "Reinhard1": 2}
+COLORSPACES = {"sRGB": 0, "Rec709": 1, "Rec2020": 2}
+
+
+def output_settings(rs: RenderSettings, factor: float = 1.0) -> "ffi.RptOutputSettings":
+    """TonemapSettings + ColorSpaceSettings of a render setting (reference src/parsing/tonemap.rs:9-31,
+    src/parsing/config.rs:33-43) -> RptOutputSettings; factor is multiplied by `premultiply` as in
+    output_film (src/renderer/mod.rs:25)."""
+    tm = rs.raw.get("tonemap_settings", {"type": "Clamp", "luminance_only": True})
+    cs = rs.raw.get("colorspace_settings", {"type": "sRGB"})
+    o = ffi.RptOutputSettings()
+    o.tonemapper = TONEMAPPERS[tm["type"]]
+    o.luminance_only = int(bool(tm.get("luminance_only", True)))
+    o.exposure = float(tm.get("exposure") or 0.0)
+    o.key_value = float(tm.get("key_value", 0.18))
+    o.white_point = float(tm.get("white_point", 1.0))
+    o.colorspace = COLORSPACES[cs["type"]]
+    o.factor = float(factor) * float(rs.premultiply if rs.premultiply is not None else 1.0)
+    return o
+
+
 def split_spp(total: int, world_size: int, rank: int) -> Tuple[int, int]:
     """(count, offset) of the samples-per-pixel share of `rank` (remainder to low ranks)."""
     base, rem = divmod(total, world_size)
@@ -106,8 +127,9 @@ class CudaRenderer:
         """-> (film (H, W, 4) float32 mean XYZ, counters). One C-ABI call; host film out."""
         return scene.render_pt(st.params(self.seed, spp, spp_offset, spp_total))
 
-    def render(self, world: W.World, config: Config) -> Dict[str, np.ndarray]:
-        """trait Renderer::render: one film per render setting, keyed by filename."""
+    def render(self, world: W.World, config: Config, output_dir: Optional[str] = None) -> Dict[str, np.ndarray]:
+        """trait Renderer::render: one film per render setting, keyed by filename. With output_dir, each film also goes
+        through output_film (tonemap + colour space on the device) and is written as <filename>.png (+ linear .npy)."""
         films = {}
         scenes: Dict[Tuple[float, float], ffi.Scene] = {}
         for i, rs in enumerate(config.render_settings):
@@ -116,9 +138,30 @@ class CudaRenderer:
                 scenes[st.wavelength_bounds] = self.make_scene(world, st.wavelength_bounds)
             film, _ = self.render_sampled(scenes[st.wavelength_bounds], st)
             films[rs.filename or f"render_{i}"] = film
+            if output_dir is not None:
+                self.output_film(scenes[st.wavelength_bounds], rs, film, output_dir)
         for s in scenes.values():
             s.close()
         return films
+
+    def output_film(self, scene: ffi.Scene, rs: RenderSettings, film: Optional[np.ndarray], output_dir: Optional[str] = None, factor: float = 1.0):
+        """output_film (reference src/renderer/mod.rs:24-80) with the tonemapping / colour conversion / byte encoding on the
+        device. film=None tonemaps the device-resident film of the scene's last render. File encoding stays on the host:
+        PNG through Pillow when present; the EXR payload (linear RGB) is saved as .npy (no EXR encoder in this image)."""
+        rgb, rgba, lw = scene.output_film(output_settings(rs, factor), film, rs.width, rs.height)
+        if output_dir is not None:
+            import os
+
+            os.makedirs(output_dir, exist_ok=True)
+            name = rs.filename or "beauty"
+            np.save(os.path.join(output_dir, name + ".linear_rgb.npy"), rgb)
+            try:
+                from PIL import Image
+
+                Image.fromarray(rgba, "RGBA").save(os.path.join(output_dir, name + ".png"))
+            except ImportError:
+                np.save(os.path.join(output_dir, name + ".rgba8.npy"), rgba)
+        return rgb, rgba, lw
 
     # ---- multi-GPU: spp split + one NCCL reduce of the XYZ film (SURVEY §8e) -----------------------
     def render_sampled_distributed(self, scene: ffi.Scene, st: PTSettings, rank: int, world_size: int):

@@ -176,6 +176,42 @@ def test_public_api_render(pkg):
     os_.close()
 
 
+@pytest.mark.parametrize("tm", ["Clamp", "Reinhard0", "Reinhard1"])
+@pytest.mark.parametrize("lum_only", [True, False])
+@pytest.mark.parametrize("cs", ["sRGB", "Rec2020"])
+def test_output_film(scenes, pkg, tm, lum_only, cs):
+    """N2: device output_film (tonemapper initialize + map, XYZ->RGB, OETF, bytes) vs the oracle's sequential restatement.
+    Tolerance: linear RGB rtol 1e-5; log-average rel 1e-4 (parallel double sum vs sequential f32/f64); PNG bytes equal on
+    >= 99.5 % of channels and never more than 1 apart (powf / logf ulps on a ceil() boundary)."""
+    st, cs_gpu, cs_or = scenes("cornell", 160, 90, 16)
+    film, _ = cs_or.render_pt(st.params(seed=31))
+    film[3, 5, :3] = np.nan  # a poisoned pixel exercises the MAUVE substitution
+    o = pkg.ffi.RptOutputSettings()
+    o.tonemapper, o.luminance_only = pkg.renderer.TONEMAPPERS[tm], int(lum_only)
+    o.exposure, o.key_value, o.white_point = 4.0, 0.18, 2.0
+    o.colorspace, o.factor = pkg.renderer.COLORSPACES[cs], 1.5
+    rg, bg, lg = cs_gpu.output_film(o, film, st.width, st.height)
+    ro, bo, lo = cs_or.output_film(o, film, st.width, st.height)
+    ok = np.isfinite(ro)
+    assert np.allclose(rg[ok], ro[ok], rtol=1e-5, atol=1e-7)
+    assert np.allclose(lg, lo, rtol=1e-4)
+    d = np.abs(bg.astype(np.int32) - bo.astype(np.int32))
+    assert d.max() <= 1 and float(np.mean(d == 0)) >= 0.995, (d.max(), float(np.mean(d == 0)))
+    assert (bg[..., 3] == 255).all() and bg[..., :3].max() > 0
+
+
+def test_output_film_from_device_resident_film(scenes, pkg):
+    """film=None tonemaps the film the last render left on the device: same bytes as passing the downloaded film."""
+    st, cs_gpu, _ = scenes("cornell", 160, 90, 16)
+    film, _ = cs_gpu.render_pt(st.params(seed=5))
+    o = pkg.ffi.RptOutputSettings()
+    o.tonemapper, o.luminance_only, o.key_value, o.white_point, o.colorspace, o.factor = 2, 0, 0.18, 1.0, 2, 1.0
+    _, b_host, _ = cs_gpu.output_film(o, film, st.width, st.height)
+    cs_gpu.render_pt(st.params(seed=5))
+    _, b_dev, _ = cs_gpu.output_film(o, None, st.width, st.height)
+    assert float(np.mean(b_host == b_dev)) > 0.999  # energy atomics reorder between the two renders
+
+
 def test_tma_tile_variant(monkeypatch):
     """k_trace with TMA-staged queue tiles (cp.async.bulk + mbarrier, RPT_TMA_TILES=1) is bit-identical to the default."""
     world, st, flat = parity.load_scene("cornell", 160, 90, 4)

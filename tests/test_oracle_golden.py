@@ -217,3 +217,28 @@ def test_oracle_furnace_energy(pkg):
     centre = float(film[28:36, 28:36, 1].mean())
     assert 0.5 < centre / corner < 1.5
     sc.close()
+
+
+def test_oracle_output_film_known_answers(pkg):
+    """output_film restatement vs closed forms: Clamp per-channel = ceil(255 * OETF(M * clip(XYZ * 2^e))) and the Reinhard
+    log-average l_w = exp(mean ln(0.001 + Y)) / factor (tonemap/clamp.rs:76-101, reinhard0.rs:48-73, mod.rs:147-205,314-331)."""
+    import parity
+
+    world, st, flat = parity.load_scene("cornell", 8, 8, 1)
+    sc = parity.oracle_scene(flat)
+    rng = np.random.default_rng(0)
+    film = np.zeros((8, 8, 4), dtype=np.float32)
+    film[..., :3] = rng.uniform(0.0, 1.2, size=(8, 8, 3)).astype(np.float32)
+    o = pkg.ffi.RptOutputSettings()
+    o.tonemapper, o.luminance_only, o.exposure, o.colorspace, o.factor = 0, 0, 0.0, 0, 1.0
+    rgb, rgba, _ = sc.output_film(o, film, 8, 8)
+    M = np.array([[3.24096994, -1.53738318, -0.49861076], [-0.96924364, 1.8759675, 0.04155506], [0.05563008, -0.20397696, 1.05697151]], dtype=np.float32)
+    lin = np.clip(film[..., :3], 0, 1) @ M.T
+    enc = np.where(lin < 0.0031308, 323.0 / 25.0 * lin, 211.0 / 200.0 * np.power(np.maximum(lin, 0), 5.0 / 12.0) - 11.0 / 200.0)
+    want = np.clip(np.ceil(enc * 255.0), 0, 255).astype(np.uint8)
+    assert np.abs(rgba[..., :3].astype(int) - want.astype(int)).max() <= 1
+    assert np.allclose(rgb, film[..., :3] @ M.T, rtol=1e-5, atol=1e-6)
+    o.tonemapper, o.luminance_only, o.key_value, o.factor = 1, 1, 0.18, 2.0
+    _, _, lw = sc.output_film(o, film, 8, 8)
+    assert np.isclose(lw[1], np.exp(np.mean(np.log(0.001 + film[..., 1].astype(np.float64)))) / 2.0, rtol=1e-5)
+    sc.close()
