@@ -123,15 +123,19 @@ inline V3 random_in_unit_disk(float sx, float sy) {
   float v = std::sqrt(sy);
   return v3(std::cos(u) * v, std::sin(u) * v, 0.0f);
 }
+// uv <-> direction: trigonometry evaluated as correctly rounded f32 (through f64). The reference calls the platform libm
+// here (f32::sin_cos / atan2 / acos); importance-map samples sit exactly on texel boundaries, so which texel the round
+// trip uv -> direction -> uv lands in depends on the libm's last ulp. The oracle and the CUDA path both pin the
+// correctly rounded value (what glibc >= 2.41 returns), see DESIGN.md §2.
 inline V3 uv_to_direction(float u, float v) {
   float theta = (u - 0.5f) * TAU_F;
   float phi = v * PI_F;
-  float st = std::sin(theta), ctt = std::cos(theta), sp = std::sin(phi), cp = std::cos(phi);
+  float st = (float)std::sin((double)theta), ctt = (float)std::cos((double)theta), sp = (float)std::sin((double)phi), cp = (float)std::cos((double)phi);
   return v3(sp * ctt, sp * st, cp);
 }
 inline void direction_to_uv(V3 d, float &u, float &v) {
-  float theta = std::atan2(d.y, d.x);
-  float phi = std::acos(d.z);
+  float theta = (float)std::atan2((double)d.y, (double)d.x);
+  float phi = (float)std::acos((double)d.z);
   u = theta / 2.0f / PI_F + 0.5f;
   v = phi / PI_F;
 }

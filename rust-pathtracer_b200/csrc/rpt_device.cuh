@@ -86,6 +86,7 @@ struct DevScene {
   // lets the NEE visibility query run as "closest light, then any occluder in front of it" (k_shadow).
   uint32_t num_light_geom;  // 0 = two-phase NEE visibility disabled
   const uint32_t *light_geom;
+  const float *light_geom_box;  // 6 floats (world min, max) per entry: the box the reference's BVH gates the shape with
   const RptMaterial *materials;
   const float *curve_lut;
   const float *cie_lut;
@@ -184,15 +185,21 @@ __device__ __forceinline__ float3 random_in_unit_disk(float sx, float sy) {
   float v = sqrtf(sy);
   return f3(c * v, s * v, 0.0f);
 }
+// The uv <-> direction maps evaluate their trigonometry as CORRECTLY ROUNDED f32 (through f64): importance-map samples sit
+// exactly on texel boundaries (nearest-mode CDF inversion returns grid points) and then go through
+// uv -> direction -> rotate -> uv -> texel, so a 1-ulp difference between two libm implementations flips the texel that
+// is read. The reference inherits whatever the platform libm does there; both this file and the oracle pin it to the
+// correctly rounded value. Only the Sun / HDR environment paths pay for the f64 calls.
 __device__ __forceinline__ float3 uv_to_direction(float u, float v) {
-  float st, ct, sp, cp;
-  sincosf((u - 0.5f) * RPT_TAU, &st, &ct);
-  sincosf(v * RPT_PI, &sp, &cp);
-  return f3(sp * ct, sp * st, cp);
+  double st, ct, sp, cp;
+  sincos((double)((u - 0.5f) * RPT_TAU), &st, &ct);
+  sincos((double)(v * RPT_PI), &sp, &cp);
+  float fst = (float)st, fct = (float)ct, fsp = (float)sp, fcp = (float)cp;
+  return f3(fsp * fct, fsp * fst, fcp);
 }
 __device__ __forceinline__ void direction_to_uv(float3 d, float &u, float &v) {
-  float theta = atan2f(d.y, d.x);
-  float phi = acosf(d.z);
+  float theta = (float)atan2((double)d.y, (double)d.x);
+  float phi = (float)acos((double)d.z);
   u = theta / 2.0f / RPT_PI + 0.5f;
   v = phi / RPT_PI;
 }

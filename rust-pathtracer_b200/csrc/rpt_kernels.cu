@@ -686,10 +686,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
       uint64_t key_l = 0;
       bool found_l = false;
       uint32_t inst_l = RPT_NONE;
+      const float3 winv = f3(rcp_approx(d.x), rcp_approx(d.y), rcp_approx(d.z));
+      const float3 woinv = f3(o.x * winv.x, o.y * winv.y, o.z * winv.z);
       for (uint32_t k = 0; k < S.num_light_geom; ++k) {
         uint32_t li = __ldg(S.light_geom + k);
         const DevInstance &I = S.instances[li];
         uint32_t flags = I.flags;
+        if ((flags & DI_KIND_MASK) == RPT_AGG_DISK) {
+          // A disk's bounding box is SMALLER than the disk (disk.rs:23-28: half extent radius / 2), so the part of the
+          // disk outside it is unreachable through the reference's BVH; the traversal reproduces that through the leaf
+          // box, phase A has to gate on the same box.
+          const float *bx = S.light_geom_box + 6 * k;
+          float tn;
+          if (!slab_test(f3(__ldg(bx), __ldg(bx + 1), __ldg(bx + 2)), f3(__ldg(bx + 3), __ldg(bx + 4), __ldg(bx + 5)), woinv, winv, tl, tn)) continue;
+        }
         float3 lo = o, ld = d;
         if (flags & DI_HAS_TRANSFORM) {
           lo = xform_point(I.rev, o);
@@ -1563,6 +1573,11 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     }
   }
   if (!light_geom_ok || light_geom.size() > 8) light_geom.clear();
+  std::vector<float> light_geom_box;
+  for (uint32_t i : light_geom) {
+    light_geom_box.insert(light_geom_box.end(), ibox[i].mn, ibox[i].mn + 3);
+    light_geom_box.insert(light_geom_box.end(), ibox[i].mx, ibox[i].mx + 3);
+  }
 
   DevScene &D = S->dev;
   DeviceBuffers &B = S->bufs;
@@ -1574,6 +1589,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   rc |= B.upload(tri_normals.data(), tri_normals.size(), &D.tri_normals);
   rc |= B.upload(d->lights, d->num_lights, &D.lights);
   rc |= B.upload(light_geom.data(), light_geom.size(), &D.light_geom);
+  rc |= B.upload(light_geom_box.data(), light_geom_box.size(), &D.light_geom_box);
   D.num_light_geom = (uint32_t)light_geom.size();
   rc |= B.upload(d->materials, d->num_materials, &D.materials);
   rc |= B.upload(d->curve_lut, (size_t)d->num_curves * d->num_lambda, &D.curve_lut);

@@ -9,7 +9,7 @@ import parity
 pytestmark = pytest.mark.gpu
 
 ALL_SCENES = ["cornell", "furnace", "furnace_exact", "gem", "hdri", "test_nee_sphere", "orb_caustic", "sun_test",
-              "parallel_prism", "lighting_north", "rtiow2"]
+              "parallel_prism", "lighting_north", "rtiow2", "kitchen_sink"]
 
 
 @pytest.fixture(scope="module")
@@ -45,13 +45,13 @@ def test_primary_hit_ids(scenes, name):
         assert np.allclose(gt[both], ot[both], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["cornell", "gem", "test_nee_sphere", "instanced_monkeys"])
+@pytest.mark.parametrize("name", ["cornell", "gem", "test_nee_sphere", "instanced_monkeys", "kitchen_sink"])
 def test_random_rays(scenes, name):
     """Closest hits of random rays from inside the scene bounds match the oracle (ids bit-exact)."""
     st, cs, os_ = scenes(name, 64, 64, 1)
     rng = np.random.default_rng(11)
     n = 20000
-    scale = 40.0 if name == "instanced_monkeys" else 1.0
+    scale = {"instanced_monkeys": 40.0, "kitchen_sink": 3.0}.get(name, 1.0)
     o = (rng.uniform(-0.9, 0.9, size=(n, 3)) * scale).astype(np.float32)
     if name == "cornell":
         o = (rng.uniform(0.01, 0.54, size=(n, 3))).astype(np.float32)
@@ -76,6 +76,11 @@ def test_same_stream_images(scenes, name):
     assert np.isfinite(fg).all()
     assert parity.mean_rel_diff(fg, fo) < 2e-3, (name, fg[..., 1].mean(), fo[..., 1].mean())
     assert parity.rel_mse(fg, fo) < 2e-3, (name, parity.rel_mse(fg, fo))
+    # ... and the pixels that differ at all are a handful (a systematic difference - a wrong weight, a visibility rule -
+    # touches percent-level fractions of the image while staying under the relMSE bound above)
+    yg, yo = fg[..., 1], fo[..., 1]
+    differing = float(np.mean(np.abs(yg - yo) > 1e-4 * np.maximum(np.abs(yo), 1e-6)))
+    assert differing <= 5e-3, (name, differing)
     # Profile counters (profile.rs): identical up to the rare divergent paths
     for k in ("camera_rays",):
         assert getattr(cg, k) == getattr(co, k)

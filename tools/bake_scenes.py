@@ -86,6 +86,206 @@ aperture = { type = "Circular" }
 focal_distance = 5.0
 vfov = 30.0
 """)
+    # kitchen sink: every primitive / light / material kind the GPU path supports, with transforms, in one small scene
+    with open(os.path.join(GEN, "kitchen_sink.toml"), "w") as f:
+        f.write('curves = "data/lib_curves.toml"\nmeshes = "data/lib_meshes.toml"\n' + """
+env_sampling_probability = 0.3
+[environment]
+type = "Constant"
+strength = 0.004
+color = "D65"
+
+[[textures.checker]]
+type = "Texture4"
+filename = "data/textures/simple.png"
+curves = ["srgb_r", "srgb_g", "srgb_b", "flat_zero"]
+[[textures.lambertian_white]]
+type = "Texture1"
+filename = "data/textures/single_pixel.png"
+curve = "cornell_white"
+[[textures.lambertian_red]]
+type = "Texture1"
+filename = "data/textures/single_pixel.png"
+curve = "cornell_red"
+
+# floor: textured two-sided rect (uv lookup through Texture4)
+[[instances]]
+material_name = "lambertian_textured_simple"
+[instances.aggregate]
+type = "Rect"
+size = [8.0, 8.0]
+origin = [0.0, 0.0, -1.0]
+normal = "Z"
+two_sided = true
+
+# a rotated, non-uniformly scaled rect light (transform on an analytic light: instance.rs:134-170)
+[[instances]]
+material_name = "diffuse_light_warm"
+[instances.aggregate]
+type = "Rect"
+size = [1.0, 1.0]
+origin = [0.0, 0.0, 0.0]
+normal = "Y"
+two_sided = true
+[instances.transform]
+scale = [1.5, 1.0, 0.75]
+translate = [0.0, 3.0, 1.0]
+[[instances.transform.rotate]]
+axis = [0.0, 0.0, 1.0]
+angle = 25
+
+# a sphere light and a one-sided disk light with a sharp lobe
+[[instances]]
+material_name = "diffuse_light_xenon"
+[instances.aggregate]
+type = "Sphere"
+radius = 0.3
+origin = [-2.0, -1.0, 1.5]
+
+[[instances]]
+material_name = "sharp_light_warm"
+[instances.aggregate]
+type = "Disk"
+radius = 0.6
+origin = [0.8, -1.0, 1.6]
+two_sided = false
+
+# non-light disks: one-sided and two-sided, one of them tilted
+[[instances]]
+material_name = "lambertian_red"
+[instances.aggregate]
+type = "Disk"
+radius = 0.8
+origin = [2.0, 1.0, -0.2]
+two_sided = true
+[[instances]]
+material_name = "ggx_copper"
+[instances.aggregate]
+type = "Disk"
+radius = 0.7
+origin = [0.0, 0.0, 0.0]
+two_sided = false
+[instances.transform]
+translate = [-2.2, 1.6, 0.3]
+[[instances.transform.rotate]]
+axis = [1.0, 0.0, 0.0]
+angle = 40
+
+# spheres: metal, rough glass, dispersive glass, an ellipsoid through non-uniform scale
+[[instances]]
+material_name = "ggx_gold"
+[instances.aggregate]
+type = "Sphere"
+radius = 0.6
+origin = [0.3, 1.3, -0.4]
+[[instances]]
+material_name = "ggx_glass_rough"
+[instances.aggregate]
+type = "Sphere"
+radius = 0.5
+origin = [1.4, 0.2, -0.5]
+[[instances]]
+material_name = "ggx_glass_dispersive"
+[instances.aggregate]
+type = "Sphere"
+radius = 0.5
+origin = [0.0, 0.0, 0.0]
+[instances.transform]
+scale = [1.0, 0.6, 1.4]
+translate = [-1.2, -0.4, -0.3]
+[[instances.transform.rotate]]
+axis = [0.0, 1.0, 0.0]
+angle = 30
+
+# meshes with shading normals: transformed (two-level traversal) and untransformed (flattened into the TLAS)
+[[instances]]
+material_name = "ggx_moissanite"
+[instances.aggregate]
+type = "Mesh"
+name = "brilliant_diamond"
+[instances.transform]
+scale = [0.5, 0.5, 0.5]
+translate = [0.6, -1.2, -0.6]
+[[instances.transform.rotate]]
+axis = [1.0, 1.0, 0.0]
+angle = 35
+[[instances]]
+material_name = "lambertian_white"
+[instances.aggregate]
+type = "Mesh"
+name = "prism"
+
+[materials.lambertian_textured_simple]
+type = "Lambertian"
+texture_id = "checker"
+[materials.lambertian_white]
+type = "Lambertian"
+texture_id = "lambertian_white"
+[materials.lambertian_red]
+type = "Lambertian"
+texture_id = "lambertian_red"
+[materials.diffuse_light_warm]
+type = "DiffuseLight"
+sidedness = "Dual"
+emit_color = "blackbody_3000k_x5"
+bounce_color = "flat_78"
+[materials.diffuse_light_xenon]
+type = "DiffuseLight"
+sidedness = "Forward"
+emit_color = "xenon_x5"
+bounce_color = "flat_78"
+[materials.sharp_light_warm]
+type = "SharpLight"
+sidedness = "Reverse"
+sharpness = 12.0
+emit_color = "blackbody_3000k_x5"
+bounce_color = "flat_78"
+[materials.ggx_gold]
+type = "GGX"
+permeability = 0.0
+alpha = 0.05
+eta_o = "air_ior"
+eta = { type = "TabulatedCSV", filename = "data/curves/csv/gold.csv", column = 1, domain_mapping = { x_scale = 1000.0 }, interpolation_mode = "Cubic" }
+kappa = { type = "TabulatedCSV", filename = "data/curves/csv/gold.csv", column = 2, domain_mapping = { x_scale = 1000.0 }, interpolation_mode = "Cubic" }
+[materials.ggx_copper]
+type = "GGX"
+permeability = 0.0
+alpha = 0.1
+eta_o = "air_ior"
+eta = { type = "TabulatedCSV", filename = "data/curves/csv/copper-mcpeak.csv", column = 1, domain_mapping = { x_scale = 1000.0 }, interpolation_mode = "Cubic" }
+kappa = { type = "TabulatedCSV", filename = "data/curves/csv/copper-mcpeak.csv", column = 2, domain_mapping = { x_scale = 1000.0 }, interpolation_mode = "Cubic" }
+[materials.ggx_glass_rough]
+type = "GGX"
+permeability = 1.0
+alpha = 0.2
+kappa = "flat_zero"
+eta_o = "air_ior"
+eta = { type = "Cauchy", a = 1.4, b = 10000.0 }
+[materials.ggx_glass_dispersive]
+type = "GGX"
+permeability = 1.0
+alpha = 0.01
+kappa = "flat_zero"
+eta_o = "air_ior"
+eta = { type = "Cauchy", a = 1.4, b = 30000.0 }
+[materials.ggx_moissanite]
+type = "GGX"
+permeability = 1.0
+alpha = 0.01
+kappa = "flat_zero"
+eta_o = "air_ior"
+eta = { type = "Cauchy", a = 2.4, b = 34000.0 }
+
+[[cameras]]
+type = "SimpleCamera"
+name = "main"
+look_from = [-6.0, -3.0, 2.5]
+look_at = [0.0, 0.0, -0.2]
+aperture_diameter = 0.05
+aperture = { type = "Circular" }
+focal_distance = 6.5
+vfov = 50.0
+""")
     # instanced monkeys (C5): 48 x 50 grid (minus 12) = 2388 instances, Philox-free numpy RNG seed 5
     rng = np.random.default_rng(5)
     mats = ["lambertian_white", "ggx_gold", "ggx_copper", "ggx_glass"]
@@ -189,6 +389,7 @@ def main():
         "sun_test": lambda: bake("sun_test", make_config("data/scenes/sun_test.toml", 512, 512, 32, 2, 8, 2)),
         "parallel_prism": lambda: bake("parallel_prism", make_config("data/scenes/cornell_box_parallel_prism.toml", 512, 512, 32, 2, 10, 2)),
         "lighting_north": lambda: bake("lighting_north", from_reference_config("data/config_test_lighting_north.toml")),
+        "kitchen_sink": lambda: bake("kitchen_sink", make_config("data/scenes/kitchen_sink.toml", 512, 384, 32, 2, 10, 3)),
         "rtiow2": lambda: bake("rtiow2", make_config("data/scenes/test_rtiow_scene_2.toml", 512, 512, 32, 2, 8, 2)),
     }
     for name, job in jobs.items():

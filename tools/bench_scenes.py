@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import parity
 
-DEFAULT = ["cornell", "furnace", "gem", "hdri", "instanced_monkeys", "test_nee_sphere", "orb_caustic", "sun_test", "rtiow2"]
+DEFAULT = ["cornell", "furnace", "gem", "hdri", "instanced_monkeys", "test_nee_sphere", "orb_caustic", "sun_test", "rtiow2", "kitchen_sink"]
 SPP_CAP = {"gem": 64}  # 1080p @ 1024 spp is 2.1 G samples: time 64 spp (one wave), the rate is spp-independent
 names = sys.argv[1:] or DEFAULT
 print("| scene | film | spp | ms | Msamples/s | Gsegments/s | Grays/s (reference def.) | Grays/s (true) | nodes/ray walk | tris/ray walk | insts/ray walk | nodes/ray NEE | top kernels |")

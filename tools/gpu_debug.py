@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import parity
 
-names = sys.argv[1:] or ["cornell", "furnace", "furnace_exact", "gem", "hdri", "test_nee_sphere", "orb_caustic", "sun_test", "parallel_prism", "lighting_north", "rtiow2", "instanced_monkeys"]
+names = sys.argv[1:] or ["cornell", "furnace", "furnace_exact", "gem", "hdri", "test_nee_sphere", "orb_caustic", "sun_test", "parallel_prism", "lighting_north", "rtiow2", "instanced_monkeys", "kitchen_sink"]
 for name in names:
     try:
         w, h = (192, 108)
