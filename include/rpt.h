@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RPT_ABI_VERSION 5u
+#define RPT_ABI_VERSION 6u
 
 /* ---- MaterialId (reference src/materials/mod.rs:22-27) --------------------------
  * Packed as (tag << 16) | table_index; RPT_MAT_NONE = "no override / no id". */
@@ -284,6 +284,30 @@ typedef struct RptOutputSettings {
  * l_w: optional out, the 4 lanes of the tonemapper's log-average (lane 0..2 = X,Y,Z for x3 variants; Y only else). */
 int rpt_output_film(RptScene *scene, const float *film_xyzw, uint32_t width, uint32_t height, const RptOutputSettings *settings,
                     float *rgb_linear, uint8_t *rgba8, float *l_w);
+
+/* ---- N3: ImportanceMap::bake_raw on the device (reference src/world/importance_map.rs:78-253) --------------------
+ * The step immediately before the hot path: for every (row, column) of the map, the luminance of the environment texel
+ * at uv = (row / rows, column / cols) (:137-140) is the num_samples-point left Riemann sum over the wavelength bounds of
+ *   Machine{1, [Mul luminance_curve, Mul texture_stack.curve_at(uv)]}          (:141-152; texture.rs:41-77,126-131,221-228)
+ * every row is normalised into a pdf and a cumulative mass function (:153-176), the row sums into the marginal (:214),
+ * and the marginal goes through Curve::to_cdf((0,1), 100) (:239-244).
+ * The curves are evaluated by the CALLER (the real math::Curve on the host side of the shim) at the sample wavelengths
+ * lambda_i = lo + i * (hi - lo) / num_samples, i < num_samples, so no curve interpolation happens on the device. */
+typedef struct RptImapBake {
+  uint32_t rows, cols;        /* vertical_resolution (index <-> u), horizontal_resolution (index <-> v) */
+  uint32_t num_samples;       /* num_samples_for_texel_spectra, 100 in the reference (:85) */
+  float lambda_lo, lambda_hi; /* wavelength_bounds */
+  const float *luminance;     /* num_samples values of luminance_curve */
+  const float *basis;         /* environment texture stack, texture k, channel c: basis[(4 * k + c) * num_samples + i]
+                                 = curves[c].pdf evaluated at lambda_i (Texture1 uses c = 0 only) */
+} RptImapBake;
+
+/* Bakes from the scene's device-resident environment texels and INSTALLS the tables in the scene (subsequent renders
+ * importance-sample the environment through them; nothing is re-uploaded). Every out pointer is optional (NULL = keep on
+ * the device only): row_pdf / row_cdf rows*cols floats, marginal_pdf / marginal_cdf rows floats, marginal_integral 1 float
+ * — exactly the payload of the reference's on-disk cache (:254-324), whose bincode encoding stays on the host. */
+int rpt_scene_bake_importance_map(RptScene *scene, const RptImapBake *bake, float *row_pdf, float *row_cdf, float *marginal_pdf,
+                                  float *marginal_cdf, float *marginal_integral);
 
 /* BVH statistics for roofline accounting: bytes of nodes / primitives. */
 typedef struct RptSceneStats {

@@ -1651,6 +1651,85 @@ int rpto_output_film(RptScene *, const float *film, uint32_t W, uint32_t H, cons
   return 0;
 }
 
+// ---- N3: ImportanceMap::bake_raw (world/importance_map.rs:78-253), scalar restatement -----------------------------
+// Curve::Machine (math crate, unpinned): seed, then every (op, curve) applied left to right, result clamped at 0.
+// Curve::evaluate_integral(bounds, n, clamped = false): left Riemann sum, f32 accumulation, times the step (unpinned).
+int rpto_scene_bake_importance_map(RptScene *S, const RptImapBake *B, float *row_pdf, float *row_cdf, float *marginal_pdf, float *marginal_cdf,
+                                   float *marginal_integral) {
+  if (!S || !B) return fail("null argument");
+  if (S->env.kind != RPT_ENV_HDR) return fail("importance maps exist for HDR environments only");
+  if (B->rows == 0 || B->cols == 0 || B->num_samples == 0) return fail("empty importance map");
+  const uint32_t R = B->rows, Cn = B->cols, NS = B->num_samples;
+  const RptTexStack &st = S->stacks[S->env.texstack];
+  const float step = (B->lambda_hi - B->lambda_lo) / (float)NS;
+  std::vector<float> lum((size_t)R * Cn), row_sum(R);
+  S->imap_row_pdf.assign((size_t)R * Cn, 0.0f);
+  S->imap_row_cdf.assign((size_t)R * Cn, 0.0f);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t row = 0; row < (int64_t)R; ++row) {
+    float row_luminance = 0.0f;
+    for (uint32_t col = 0; col < Cn; ++col) {
+      float u = (float)row / (float)R, v = (float)col / (float)Cn;  // :137-140
+      float sum = 0.0f;
+      for (uint32_t i = 0; i < NS; ++i) {
+        float stack = 0.0f;  // TexStack::curve_at: Machine{0, [Add tex.curve_at(uv)]} (texture.rs:221-228)
+        for (uint32_t k = 0; k < st.count; ++k) {
+          const OTexture &T = S->textures[S->stack_tex[st.first + k]];
+          float uu = clampf(u, 0.0f, 1.0f - EPS_F), vv = clampf(v, 0.0f, 1.0f - EPS_F);  // vec2d.rs:34-42
+          size_t x = (size_t)(uu * (float)T.w), y = (size_t)(vv * (float)T.h);
+          const float *tx = &T.texels[(y * T.w + x) * T.channels];
+          const float *bs = B->basis + (size_t)(4 * k) * NS;
+          float tv;
+          if (T.channels == 1) {
+            tv = std::fmax(tx[0] * bs[i], 0.0f);  // Texture1::curve_at: Machine{texel, [Mul curve]} (texture.rs:126-131)
+          } else {
+            tv = 0.0f;  // Texture4::curve_at: Machine{0, [Add Machine{texel[c], [Mul curves[c]]}]} (texture.rs:41-77)
+            for (int c = 0; c < 4; ++c) tv = tv + std::fmax(tx[c] * bs[(size_t)c * NS + i], 0.0f);
+            tv = std::fmax(tv, 0.0f);
+          }
+          stack = stack + tv;
+        }
+        stack = std::fmax(stack, 0.0f);
+        sum += std::fmax(1.0f * B->luminance[i] * stack, 0.0f);  // Machine{1, [Mul luminance, Mul stack curve]} (:141-147)
+      }
+      float texel_luminance = sum * step;
+      row_luminance += texel_luminance;  // :153
+      lum[(size_t)row * Cn + col] = texel_luminance;
+      S->imap_row_cdf[(size_t)row * Cn + col] = row_luminance;
+    }
+    for (uint32_t col = 0; col < Cn; ++col) {  // :158-163 (a black row divides 0 by 0, as the reference does)
+      S->imap_row_pdf[(size_t)row * Cn + col] = lum[(size_t)row * Cn + col] / row_luminance;
+      S->imap_row_cdf[(size_t)row * Cn + col] /= row_luminance;
+    }
+    row_sum[row] = row_luminance;
+  }
+  float total = 0.0f;
+  for (uint32_t r = 0; r < R; ++r) total += row_sum[r];  // :199
+  S->imap_m_pdf.resize(R);
+  S->imap_m_cdf.resize(R);
+  for (uint32_t r = 0; r < R; ++r) S->imap_m_pdf[r] = row_sum[r] / total;  // :214
+  // Curve::Linear::to_cdf (math crate, unpinned): running sum of signal * step over the curve's own samples, normalised
+  float mstep = (1.0f - 0.0f) / (float)R, acc = 0.0f;
+  for (uint32_t r = 0; r < R; ++r) {
+    acc += S->imap_m_pdf[r] * mstep;
+    S->imap_m_cdf[r] = acc;
+  }
+  float integral = acc;
+  for (uint32_t r = 0; r < R; ++r) S->imap_m_cdf[r] /= integral;
+  S->env.imap_rows = R;
+  S->env.imap_cols = Cn;
+  S->env.imap_marginal_n = R;
+  S->env.imap_marginal_integral = integral;
+  size_t n = (size_t)R * Cn;
+  if (row_pdf) std::copy(S->imap_row_pdf.begin(), S->imap_row_pdf.end(), row_pdf);
+  if (row_cdf) std::copy(S->imap_row_cdf.begin(), S->imap_row_cdf.end(), row_cdf);
+  if (marginal_pdf) std::copy(S->imap_m_pdf.begin(), S->imap_m_pdf.end(), marginal_pdf);
+  if (marginal_cdf) std::copy(S->imap_m_cdf.begin(), S->imap_m_cdf.end(), marginal_cdf);
+  if (marginal_integral) *marginal_integral = integral;
+  (void)n;
+  return 0;
+}
+
 // ---- unit hooks for the known-answer tests (tests/test_oracle_*.py) ----------------------------------------
 // ggx_glass(roughness) of the reference's tests: eta = cauchy(1.5, 10000), eta_o = 1, kappa = 0 (ggx.rs:630-635)
 void rpto_ggx_bsdf(float alpha, float eta_inner, float eta_outer, float kappa, int metallic, const float *wi, const float *wo, float *f, float *pdf) {

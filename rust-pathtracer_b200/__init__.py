@@ -9,7 +9,7 @@ flattening), loader.py / curves.py / world.py / importance_map.py (host mirror o
 parsing + World), renderer.py (`CudaRenderer`, the mirror of the reference's `Renderer` trait),
 blob.py (portable flattened scenes).
 """
-from . import blob, curves, ffi, loader, renderer, world  # noqa: F401
+from . import blob, curves, ffi, importance_map, loader, renderer, world  # noqa: F401
 from .renderer import CudaRenderer, PTSettings, split_spp  # noqa: F401
 
-__all__ = ["blob", "curves", "ffi", "loader", "renderer", "world", "CudaRenderer", "PTSettings", "split_spp"]
+__all__ = ["blob", "curves", "ffi", "importance_map", "loader", "renderer", "world", "CudaRenderer", "PTSettings", "split_spp"]

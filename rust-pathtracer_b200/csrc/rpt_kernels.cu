@@ -858,6 +858,81 @@ __global__ void k_out_seqsum(const float *__restrict__ logs, uint64_t n, double 
   }
 }
 
+// ---- N3: ImportanceMap::bake_raw (world/importance_map.rs:78-253) ---------------------------------------------
+// One thread per texel of the map: the 100-sample spectral integral of luminance(lambda) * texture_stack.curve_at(uv)(lambda)
+// with the Machine clamps in their reference places (see include/rpt.h). Texels come from the scene's resident
+// environment textures; curves arrive pre-evaluated at the sample wavelengths.
+__global__ void __launch_bounds__(256) k_imap_texel(DevScene S, uint32_t rows, uint32_t cols, uint32_t ns, float step,
+                                                    const float *__restrict__ lum, const float *__restrict__ basis, float *__restrict__ texel_lum) {
+  const RptTexStack st = S.stacks[S.env_texstack];
+  const uint64_t n = (uint64_t)rows * cols, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+    uint32_t row = (uint32_t)(idx / cols), col = (uint32_t)(idx % cols);
+    float u = (float)row / (float)rows, v = (float)col / (float)cols;  // :137-140
+    float uu = clampf(u, 0.0f, 1.0f - RPT_EPS), vv = clampf(v, 0.0f, 1.0f - RPT_EPS);  // vec2d.rs:34-42
+    float sum = 0.0f;
+    for (uint32_t i = 0; i < ns; ++i) {
+      float stack = 0.0f;
+      for (uint32_t k = 0; k < st.count; ++k) {
+        const DevTexture &T = S.textures[S.stack_tex[st.first + k]];
+        size_t x = (size_t)(uu * (float)T.width), y = (size_t)(vv * (float)T.height);
+        const float *tx = T.texels + (y * T.width + x) * T.channels;
+        const float *bs = basis + (size_t)(4 * k) * ns;
+        float tv;
+        if (T.channels == 1) {
+          tv = fmaxf(__ldg(tx) * __ldg(bs + i), 0.0f);
+        } else {
+          tv = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tv = tv + fmaxf(__ldg(tx + c) * __ldg(bs + (size_t)c * ns + i), 0.0f);
+          tv = fmaxf(tv, 0.0f);
+        }
+        stack = stack + tv;
+      }
+      stack = fmaxf(stack, 0.0f);
+      sum += fmaxf(1.0f * __ldg(lum + i) * stack, 0.0f);
+    }
+    texel_lum[idx] = sum * step;
+  }
+}
+
+// One thread per row: the reference accumulates the row mass sequentially in f32 (:153-156); a parallel scan would round
+// differently, and 1024 dependent adds per row are nothing. Then the per-row normalisation (:158-163).
+__global__ void __launch_bounds__(128) k_imap_rows(uint32_t rows, uint32_t cols, const float *__restrict__ texel_lum, float *__restrict__ row_pdf,
+                                                   float *__restrict__ row_cdf, float *__restrict__ row_sum) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const float *src = texel_lum + (size_t)row * cols;
+  float *pdf = row_pdf + (size_t)row * cols, *cdf = row_cdf + (size_t)row * cols;
+  float acc = 0.0f;
+  for (uint32_t c = 0; c < cols; ++c) {
+    acc += src[c];
+    cdf[c] = acc;
+  }
+  for (uint32_t c = 0; c < cols; ++c) {
+    pdf[c] = src[c] / acc;
+    cdf[c] = cdf[c] / acc;
+  }
+  row_sum[row] = acc;
+}
+
+// Marginal: row sums / total (:199,214) and Curve::Linear::to_cdf (:239-244). Sequential by definition, one thread.
+__global__ void k_imap_marginal(uint32_t rows, const float *__restrict__ row_sum, float *__restrict__ m_pdf, float *__restrict__ m_cdf,
+                                float *__restrict__ integral_out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  float total = 0.0f;
+  for (uint32_t r = 0; r < rows; ++r) total += row_sum[r];
+  float mstep = (1.0f - 0.0f) / (float)rows, acc = 0.0f;
+  for (uint32_t r = 0; r < rows; ++r) {
+    float p = row_sum[r] / total;
+    m_pdf[r] = p;
+    acc += p * mstep;
+    m_cdf[r] = acc;
+  }
+  for (uint32_t r = 0; r < rows; ++r) m_cdf[r] = m_cdf[r] / acc;
+  *integral_out = acc;
+}
+
 __device__ __forceinline__ float oetf_dev(float v, uint32_t cs) {
   if (cs == RPT_COLORSPACE_SRGB) return v < 0.0031308f ? (323.0f / 25.0f) * v : (211.0f / 200.0f) * powf(v, 5.0f / 12.0f) - (11.0f / 200.0f);
   return v < 0.01805397f ? 4.5f * v : 1.0992968f * powf(v, 0.45f) - 0.09929682f;
@@ -992,6 +1067,7 @@ struct RptScene {
   int grid[K_NUM] = {0};
   uint32_t stack_entries = 16;
   size_t stack_smem = 0;
+  uint32_t env_stack_count = 0;  // textures in the environment's stack (HDR)
   bool tma_tiles = false;  // k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
   // timing of the last render
   std::vector<cudaEvent_t> ev_pool;
@@ -1626,6 +1702,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   D.env_angular_diameter = E.angular_diameter;
   D.env_sun_dir = make_float3(E.sun_direction[0], E.sun_direction[1], E.sun_direction[2]);
   D.env_texstack = E.texstack;
+  if (E.kind == RPT_ENV_HDR && E.texstack >= 0 && (uint32_t)E.texstack < d->num_texstacks) S->env_stack_count = d->texstacks[E.texstack].count;
   to3x4(E.rot_forward, D.env_rot_fwd);
   to3x4(E.rot_reverse, D.env_rot_rev);
   if (E.kind == RPT_ENV_HDR && E.imap_rows) {
@@ -1839,6 +1916,64 @@ int rpt_last_kernel_times(RptScene *S, RptKernelTime *out, uint32_t cap, uint32_
     ++k;
   }
   *n = k;
+  return 0;
+}
+
+int rpt_scene_bake_importance_map(RptScene *S, const RptImapBake *B, float *row_pdf, float *row_cdf, float *marginal_pdf, float *marginal_cdf,
+                                  float *marginal_integral) {
+  if (!S || !B) return fail("null argument");
+  if (S->dev.env_kind != RPT_ENV_HDR) return fail("importance maps exist for HDR environments only (world/environment.rs:20-27)");
+  if (B->rows == 0 || B->cols == 0 || B->num_samples == 0) return fail("empty importance map");
+  if (!B->luminance || !B->basis) return fail("null curve tables");
+  CUDA_TRY(cudaSetDevice(S->device));
+  const uint32_t R = B->rows, Cn = B->cols, NS = B->num_samples;
+  const size_t n = (size_t)R * Cn;
+  const uint32_t ntex = S->env_stack_count;
+  float *d_lum = nullptr, *d_basis = nullptr, *d_texel = nullptr, *d_rowsum = nullptr, *d_integral = nullptr;
+  float *d_pdf = nullptr, *d_cdf = nullptr, *d_mpdf = nullptr, *d_mcdf = nullptr;
+  CUDA_TRY(cudaMalloc(&d_lum, NS * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_basis, (size_t)4 * ntex * NS * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_texel, n * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_rowsum, R * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_integral, sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_pdf, n * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_cdf, n * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_mpdf, R * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_mcdf, R * sizeof(float)));
+  CUDA_TRY(cudaMemcpyAsync(d_lum, B->luminance, NS * sizeof(float), cudaMemcpyHostToDevice, S->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_basis, B->basis, (size_t)4 * ntex * NS * sizeof(float), cudaMemcpyHostToDevice, S->stream));
+  const float step = (B->lambda_hi - B->lambda_lo) / (float)NS;
+  k_imap_texel<<<S->num_sms * 8, 256, 0, S->stream>>>(S->dev, R, Cn, NS, step, d_lum, d_basis, d_texel);
+  k_imap_rows<<<(R + 127) / 128, 128, 0, S->stream>>>(R, Cn, d_texel, d_pdf, d_cdf, d_rowsum);
+  k_imap_marginal<<<1, 32, 0, S->stream>>>(R, d_rowsum, d_mpdf, d_mcdf, d_integral);
+  float integral = 0.0f;
+  CUDA_TRY(cudaMemcpyAsync(&integral, d_integral, sizeof(float), cudaMemcpyDeviceToHost, S->stream));
+  if (row_pdf) CUDA_TRY(cudaMemcpyAsync(row_pdf, d_pdf, n * sizeof(float), cudaMemcpyDeviceToHost, S->stream));
+  if (row_cdf) CUDA_TRY(cudaMemcpyAsync(row_cdf, d_cdf, n * sizeof(float), cudaMemcpyDeviceToHost, S->stream));
+  if (marginal_pdf) CUDA_TRY(cudaMemcpyAsync(marginal_pdf, d_mpdf, R * sizeof(float), cudaMemcpyDeviceToHost, S->stream));
+  if (marginal_cdf) CUDA_TRY(cudaMemcpyAsync(marginal_cdf, d_mcdf, R * sizeof(float), cudaMemcpyDeviceToHost, S->stream));
+  CUDA_TRY(cudaStreamSynchronize(S->stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaFree(d_lum);
+  cudaFree(d_basis);
+  cudaFree(d_texel);
+  cudaFree(d_rowsum);
+  cudaFree(d_integral);
+  // install: the tables stay resident and replace whatever the scene was created with (old buffers live until destroy)
+  S->bufs.ptrs.push_back(d_pdf);
+  S->bufs.ptrs.push_back(d_cdf);
+  S->bufs.ptrs.push_back(d_mpdf);
+  S->bufs.ptrs.push_back(d_mcdf);
+  DevScene &D = S->dev;
+  D.imap_rows = R;
+  D.imap_cols = Cn;
+  D.imap_marginal_n = R;
+  D.imap_marginal_integral = integral;
+  D.imap_row_pdf = d_pdf;
+  D.imap_row_cdf = d_cdf;
+  D.imap_m_pdf = d_mpdf;
+  D.imap_m_cdf = d_mcdf;
+  if (marginal_integral) *marginal_integral = integral;
   return 0;
 }
 

@@ -17,7 +17,7 @@ from . import curves as C
 from . import world as W
 
 F32 = np.float32
-ABI_VERSION = 5
+ABI_VERSION = 6
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "librpt_b200.so")
@@ -120,6 +120,13 @@ class RptOutputSettings(ct.Structure):
     ]
 
 
+class RptImapBake(ct.Structure):
+    _fields_ = [
+        ("rows", c_u32), ("cols", c_u32), ("num_samples", c_u32), ("lambda_lo", c_f), ("lambda_hi", c_f),
+        ("luminance", PF), ("basis", PF),
+    ]
+
+
 class RptKernelTime(ct.Structure):
     _fields_ = [("name", ct.c_char_p), ("launches", c_u32), ("ms", c_f)]
 
@@ -135,7 +142,7 @@ class RptSceneStats(ct.Structure):
 RPT_SYMBOLS = [
     "rpt_last_error", "rpt_abi_version", "rpt_device_count", "rpt_scene_create", "rpt_scene_destroy",
     "rpt_render_pt", "rpt_render_pt_device", "rpt_trace_primary", "rpt_trace_rays", "rpt_film_scale",
-    "rpt_last_kernel_times", "rpt_scene_stats", "rpt_output_film",
+    "rpt_last_kernel_times", "rpt_scene_stats", "rpt_output_film", "rpt_scene_bake_importance_map",
 ]
 
 
@@ -406,6 +413,31 @@ class Scene:
         if fn(self.handle, fp, width, height, ct.byref(settings), vp(rgb), vp(rgba), vp(lw)) != 0:
             raise RptError(self._err())
         return rgb, rgba, lw
+
+    def bake_importance_map(self, rows: int, cols: int, luminance: np.ndarray, basis: np.ndarray, wavelength_bounds, download: bool = True):
+        """ImportanceMap::bake_raw on the device from the scene's resident environment texels (rpt.h N3); installs the tables
+        in the scene. -> dict(row_pdf, row_cdf (rows, cols), marginal_pdf, marginal_cdf (rows,), marginal_integral) when
+        download, else only marginal_integral."""
+        luminance = np.ascontiguousarray(luminance, dtype=F32)
+        basis = np.ascontiguousarray(basis, dtype=F32)
+        b = RptImapBake()
+        b.rows, b.cols, b.num_samples = rows, cols, len(luminance)
+        b.lambda_lo, b.lambda_hi = wavelength_bounds
+        b.luminance, b.basis = luminance.ctypes.data_as(PF), basis.ctypes.data_as(PF)
+        out = {}
+        ptrs = [None] * 4
+        if download:
+            out = dict(row_pdf=np.zeros((rows, cols), dtype=F32), row_cdf=np.zeros((rows, cols), dtype=F32),
+                       marginal_pdf=np.zeros(rows, dtype=F32), marginal_cdf=np.zeros(rows, dtype=F32))
+            ptrs = [out[k].ctypes.data_as(ct.c_void_p) for k in ("row_pdf", "row_cdf", "marginal_pdf", "marginal_cdf")]
+        integral = c_f()
+        fn = self._fn("scene_bake_importance_map")
+        fn.argtypes = [ct.c_void_p, ct.POINTER(RptImapBake)] + [ct.c_void_p] * 4 + [ct.POINTER(c_f)]
+        fn.restype = ct.c_int
+        if fn(self.handle, ct.byref(b), *ptrs, ct.byref(integral)) != 0:
+            raise RptError(self._err())
+        out["marginal_integral"] = float(integral.value)
+        return out
 
     def kernel_times(self) -> List[dict]:
         buf = (RptKernelTime * 32)()

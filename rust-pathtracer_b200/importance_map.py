@@ -59,3 +59,34 @@ def bake_importance_map(world: W.World, vertical_resolution: int, horizontal_res
     env.imap_marginal_pdf = marginal
     env.imap_marginal_cdf = cdf.cdf_signal.astype(F32)
     env.imap_marginal_integral = float(cdf.pdf_integral)
+
+
+def bake_curve_tables(world: W.World, luminance_curve: C.Curve, wavelength_bounds=C.BOUNDED_VISIBLE_RANGE, num_samples: int = 100):
+    """The host half of the device bake (include/rpt.h RptImapBake): luminance_curve and every basis curve of the
+    environment's texture stack evaluated at lambda_i = lo + i * (hi - lo) / num_samples (Curve::evaluate_integral's
+    sample points). -> (luminance (num_samples,), basis (num_textures * 4 * num_samples,))."""
+    lo, hi = wavelength_bounds
+    step = (hi - lo) / num_samples
+    lam = (lo + step * np.arange(num_samples, dtype=np.float64)).astype(F32)
+    lum = luminance_curve.evaluate(lam).astype(F32)
+    stack = world.texstacks[world.environment.texstack]
+    basis = np.zeros((len(stack), 4, num_samples), dtype=F32)
+    for k, tid in enumerate(stack):
+        tex = world.textures[tid]
+        for c in range(tex.channels):
+            basis[k, c] = world.curves[tex.curves[c]].evaluate(lam).astype(F32)
+    return lum, basis.ravel()
+
+
+def bake_importance_map_on_device(scene, world: W.World, vertical_resolution: int, horizontal_resolution: int, luminance_curve: C.Curve,
+                                  wavelength_bounds=C.BOUNDED_VISIBLE_RANGE, num_samples: int = 100, download: bool = True) -> dict:
+    """ImportanceMap::bake_raw through the C ABI (rpt_scene_bake_importance_map): texels never leave the device, the tables
+    are installed in `scene`; with download they are also mirrored into world.environment (what the reference caches on disk)."""
+    lum, basis = bake_curve_tables(world, luminance_curve, wavelength_bounds, num_samples)
+    out = scene.bake_importance_map(vertical_resolution, horizontal_resolution, lum, basis, wavelength_bounds, download)
+    if download:
+        env = world.environment
+        env.imap_row_pdf, env.imap_row_cdf = out["row_pdf"], out["row_cdf"]
+        env.imap_marginal_pdf, env.imap_marginal_cdf = out["marginal_pdf"], out["marginal_cdf"]
+        env.imap_marginal_integral = out["marginal_integral"]
+    return out

@@ -541,11 +541,13 @@ def construct_world(config: Config, scene_file: Optional[str] = None, resolver: 
             ts = len(world.texstacks) - 1
         world.environment = W.Environment(kind=2, strength=float(env["strength"]), texstack=ts, rotation=rot)
         im = env.get("importance_map")
-        if im is not None and bake_importance_map and float(env["strength"]) > 0.0:
-            from .importance_map import bake_importance_map as _bake
-
+        if im is not None and float(env["strength"]) > 0.0:
             lum = C.curve_from_data(im["luminance_curve"], resolver.text) if im.get("luminance_curve") else C.y_bar_curve()
-            _bake(world, int(im["height"]), int(im["width"]), lum, C.BOUNDED_VISIBLE_RANGE)
+            world.environment.imap_request = (int(im["height"]), int(im["width"]), lum)
+            if bake_importance_map:  # host bake; with False the request is left for CudaRenderer to bake on the device
+                from .importance_map import bake_importance_map as _bake
+
+                _bake(world, int(im["height"]), int(im["width"]), lum, C.BOUNDED_VISIBLE_RANGE)
     else:
         raise LoadError(f"unknown environment type {et}")
 

@@ -120,7 +120,16 @@ class CudaRenderer:
 
     def make_scene(self, world: W.World, wavelength_bounds: Tuple[float, float]) -> ffi.Scene:
         flat = ffi.FlatScene(world, wavelength_bounds[0], wavelength_bounds[1], self.num_lambda)
-        return ffi.Scene(self.lib, flat, self.device)
+        scene = ffi.Scene(self.lib, flat, self.device)
+        env = world.environment
+        if env.kind == 2 and env.imap_row_pdf is None and env.imap_request is not None:
+            # phase 2 of NaiveRenderer::render (src/renderer/naive.rs:469-487): an HDR environment whose importance map is
+            # still unbaked is baked before rendering - here on the device, from the texels the scene just uploaded
+            from .importance_map import bake_importance_map_on_device
+
+            rows, cols, lum = env.imap_request
+            bake_importance_map_on_device(scene, world, rows, cols, lum, wavelength_bounds, download=False)
+        return scene
 
     def render_sampled(self, scene: ffi.Scene, st: PTSettings, spp: Optional[int] = None, spp_offset: int = 0,
                        spp_total: Optional[int] = None):

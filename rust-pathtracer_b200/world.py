@@ -168,6 +168,8 @@ class Environment:
     imap_marginal_pdf: Optional[np.ndarray] = None
     imap_marginal_cdf: Optional[np.ndarray] = None
     imap_marginal_integral: float = 1.0
+    # ImportanceMap::Unbaked request of the scene file: (vertical_resolution, horizontal_resolution, luminance Curve)
+    imap_request: Optional[tuple] = None
 
 
 @dataclass

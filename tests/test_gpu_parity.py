@@ -181,6 +181,73 @@ def test_public_api_render(pkg):
     os_.close()
 
 
+def test_importance_map_bake_on_device(pkg):
+    """N3: rpt_scene_bake_importance_map from the scene's resident environment texels == the oracle's scalar restatement,
+    bit for bit (same f32 operation order, no FMA contraction), for the map size of hdri_test.toml and an odd one; the
+    baked tables are installed: renders that follow sample the environment through them on both sides."""
+    import parity
+
+    world, st, flat = parity.load_scene("hdri", 96, 54, 8)
+    e = world.environment
+    host = {"row_pdf": e.imap_row_pdf, "row_cdf": e.imap_row_cdf, "marginal_pdf": e.imap_marginal_pdf, "marginal_cdf": e.imap_marginal_cdf}
+    cs, os_ = parity.cuda_scene(flat), parity.oracle_scene(flat)
+    lum, basis = pkg.importance_map.bake_curve_tables(world, pkg.curves.y_bar_curve(), st.wavelength_bounds)
+    for rows, cols in ((e.imap_row_pdf.shape), (77, 130)):
+        g = cs.bake_importance_map(rows, cols, lum, basis, st.wavelength_bounds)
+        o = os_.bake_importance_map(rows, cols, lum, basis, st.wavelength_bounds)
+        for k in ("row_pdf", "row_cdf", "marginal_pdf", "marginal_cdf"):
+            assert np.array_equal(g[k], o[k]), (rows, cols, k, np.max(np.abs(g[k] - o[k])))
+        assert g["marginal_integral"] == o["marginal_integral"]
+        if (rows, cols) == e.imap_row_pdf.shape:
+            for k, r in host.items():  # and the vectorised f64 host bake agrees to f32 accumulation error
+                assert np.allclose(g[k], r, rtol=2e-5, atol=1e-9), k
+        p = st.params(seed=21)
+        fg, cg = cs.render_pt(p)
+        fo, co = os_.render_pt(p)
+        assert parity.rel_mse(fg, fo) < 1e-6, (rows, cols, parity.rel_mse(fg, fo))
+        assert cg.shadow_rays == co.shadow_rays
+    # device-only bake (nothing downloaded) leaves the same tables installed
+    f_before, _ = cs.render_pt(st.params(seed=22))
+    cs.bake_importance_map(77, 130, lum, basis, st.wavelength_bounds, download=False)
+    f_after, _ = cs.render_pt(st.params(seed=22))
+    assert parity.rel_mse(f_after, f_before) < 1e-10  # (atomic accumulation order: not bit-identical run to run)
+    cs.close()
+    os_.close()
+    # a scene without an HDR environment refuses
+    world2, st2, flat2 = parity.load_scene("cornell", 32, 18, 1)
+    c2 = parity.cuda_scene(flat2)
+    with pytest.raises(pkg.ffi.RptError):
+        c2.bake_importance_map(8, 8, lum, basis[:400], st2.wavelength_bounds)
+    c2.close()
+
+
+def test_public_api_bakes_unbaked_importance_map_on_device(pkg):
+    """CudaRenderer.make_scene repeats phase 2 of NaiveRenderer::render (naive.rs:469-487): an HDR environment whose
+    importance map is still Unbaked is baked before rendering - on the device. Same film as with the host-baked tables
+    up to the f32-vs-f64 bake difference (a handful of CDF bins move by an ulp)."""
+    import parity
+
+    world, st, flat = parity.load_scene("hdri", 64, 36, 8)
+    e = world.environment
+    r = pkg.CudaRenderer(device=0, seed=4)
+    s_host = r.make_scene(world, st.wavelength_bounds)
+    f_host, _ = r.render_sampled(s_host, st)
+    s_host.close()
+    rows, cols = e.imap_row_pdf.shape
+    e.imap_row_pdf = e.imap_row_cdf = e.imap_marginal_pdf = e.imap_marginal_cdf = None
+    e.imap_request = (rows, cols, pkg.curves.y_bar_curve())
+    s_dev = r.make_scene(world, st.wavelength_bounds)
+    f_dev, _ = r.render_sampled(s_dev, st)
+    s_dev.close()
+    assert abs(f_dev[..., 1].mean() - f_host[..., 1].mean()) / f_host[..., 1].mean() < 2e-2
+    # without a map the environment would be sampled uniformly: the films differ visibly from the importance-sampled one
+    e.imap_request = None
+    s_uni = r.make_scene(world, st.wavelength_bounds)
+    f_uni, _ = r.render_sampled(s_uni, st)
+    s_uni.close()
+    assert parity.rel_mse(f_dev, f_host) < parity.rel_mse(f_uni, f_host)
+
+
 @pytest.mark.parametrize("tm", ["Clamp", "Reinhard0", "Reinhard1"])
 @pytest.mark.parametrize("lum_only", [True, False])
 @pytest.mark.parametrize("cs", ["sRGB", "Rec2020"])

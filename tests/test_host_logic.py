@@ -143,6 +143,36 @@ def test_importance_map_tables(pkg):
     assert np.isclose(e.imap_marginal_integral, 1.0 / len(e.imap_marginal_pdf), rtol=1e-3)
 
 
+def test_importance_map_bake_restatements_agree(pkg, oracle):
+    """N3: the oracle's scalar f32 ImportanceMap::bake_raw (importance_map.rs:78-253: 100-sample Riemann sum per texel,
+    sequential row mass, to_cdf marginal) against the vectorised f64 host bake that uses linearity in the texel channels.
+    Tolerance 2e-5 relative: f32 accumulation over 100 + 1024 terms."""
+    import parity
+
+    world, st, flat = parity.load_scene("hdri", 32, 18, 1)
+    e = world.environment
+    rows, cols = e.imap_row_pdf.shape
+    ref = {"row_pdf": e.imap_row_pdf, "row_cdf": e.imap_row_cdf, "marginal_pdf": e.imap_marginal_pdf, "marginal_cdf": e.imap_marginal_cdf}
+    os_ = parity.oracle_scene(flat)
+    lum, basis = pkg.importance_map.bake_curve_tables(world, pkg.curves.y_bar_curve(), st.wavelength_bounds)
+    assert lum.shape == (100,) and basis.shape == (len(world.texstacks[e.texstack]) * 4 * 100,)
+    out = os_.bake_importance_map(rows, cols, lum, basis, st.wavelength_bounds)
+    for k, r in ref.items():
+        assert np.allclose(out[k], r, rtol=2e-5, atol=1e-9), k
+    assert np.isclose(out["marginal_integral"], e.imap_marginal_integral, rtol=1e-5)
+    assert np.all(out["row_cdf"][:, -1] == 1.0) and out["marginal_cdf"][-1] == 1.0  # x / x
+    # a smaller map over the same texels: resolution is a free parameter of the bake (hdri_test.toml:14-16)
+    small = os_.bake_importance_map(64, 48, lum, basis, st.wavelength_bounds)
+    assert small["row_pdf"].shape == (64, 48) and np.allclose(small["row_pdf"].sum(axis=1), 1.0, atol=1e-4)
+    # only HDR environments carry a map
+    world2, st2, flat2 = parity.load_scene("cornell", 32, 18, 1)
+    o2 = parity.oracle_scene(flat2)
+    with pytest.raises(pkg.ffi.RptError):
+        o2.bake_importance_map(8, 8, lum, basis[:400], st2.wavelength_bounds)
+    o2.close()
+    os_.close()
+
+
 def test_distributed_spp_split_reduce_gloo(tmp_path):
     """N > 1 path on CPU: two gloo ranks each render their spp share (CPU oracle as the stand-in renderer for the
     host logic), one reduce(sum) to rank 0, normalise: equals the single-rank render of all samples."""
