@@ -123,17 +123,29 @@ inline V3 random_in_unit_disk(float sx, float sy) {
   float v = std::sqrt(sy);
   return v3(std::cos(u) * v, std::sin(u) * v, 0.0f);
 }
-// uv <-> direction: trigonometry evaluated as correctly rounded f32 (through f64). The reference calls the platform libm
-// here (f32::sin_cos / atan2 / acos); importance-map samples sit exactly on texel boundaries, so which texel the round
-// trip uv -> direction -> uv lands in depends on the libm's last ulp. The oracle and the CUDA path both pin the
-// correctly rounded value (what glibc >= 2.41 returns), see DESIGN.md §2.
 inline V3 uv_to_direction(float u, float v) {
+  float theta = (u - 0.5f) * TAU_F;
+  float phi = v * PI_F;
+  float st = std::sin(theta), ctt = std::cos(theta), sp = std::sin(phi), cp = std::cos(phi);
+  return v3(sp * ctt, sp * st, cp);
+}
+inline void direction_to_uv(V3 d, float &u, float &v) {
+  float theta = std::atan2(d.y, d.x);
+  float phi = std::acos(d.z);
+  u = theta / 2.0f / PI_F + 0.5f;
+  v = phi / PI_F;
+}
+// The same maps with correctly rounded f32 trigonometry (through f64), used by the HDR environment only. The reference
+// calls the platform libm (f32::sin_cos / atan2 / acos); importance-map samples sit exactly on texel boundaries, so which
+// texel the round trip uv -> direction -> uv lands in depends on the libm's last ulp. The oracle and the CUDA path both
+// pin the correctly rounded value (what glibc >= 2.41 returns), see DESIGN.md §3.
+inline V3 uv_to_direction_cr(float u, float v) {
   float theta = (u - 0.5f) * TAU_F;
   float phi = v * PI_F;
   float st = (float)std::sin((double)theta), ctt = (float)std::cos((double)theta), sp = (float)std::sin((double)phi), cp = (float)std::cos((double)phi);
   return v3(sp * ctt, sp * st, cp);
 }
-inline void direction_to_uv(V3 d, float &u, float &v) {
+inline void direction_to_uv_cr(V3 d, float &u, float &v) {
   float theta = (float)std::atan2((double)d.y, (double)d.x);
   float phi = (float)std::acos((double)d.z);
   u = theta / 2.0f / PI_F + 0.5f;
@@ -1003,10 +1015,10 @@ inline float env_emission(const RptScene &S, float u, float v, float lambda) {  
       return 0.0f;
     }
     default: {
-      V3 dir = uv_to_direction(u, v);
+      V3 dir = uv_to_direction_cr(u, v);
       V3 nd = mul_vec(*reinterpret_cast<const Mat4 *>(E.rot_reverse), dir);
       float uu, vv;
-      direction_to_uv(nd, uu, vv);
+      direction_to_uv_cr(nd, uu, vv);
       return texstack_eval(S, E.texstack, lambda, uu, vv) * E.strength;
     }
   }
@@ -1024,10 +1036,10 @@ inline float env_pdf_for(const RptScene &S, float u, float v) {  // :198-258
     }
     default: {
       if (E.imap_rows == 0) return 1.0f / (4.0f * PI_F);
-      V3 dir = uv_to_direction(u, v);
+      V3 dir = uv_to_direction_cr(u, v);
       V3 nd = mul_vec(*reinterpret_cast<const Mat4 *>(E.rot_reverse), dir);
       float uu, vv;
-      direction_to_uv(nd, uu, vv);
+      direction_to_uv_cr(nd, uu, vv);
       float m = linear_curve_eval(S.imap_m_pdf.data(), E.imap_marginal_n, 0.0f, 1.0f, MODE_NEAREST, uu);
       uint32_t row = (uint32_t)(clampf(uu, 0.0f, 1.0f - EPS_F) * (float)E.imap_rows);
       float r = linear_curve_eval(&S.imap_row_pdf[(size_t)row * E.imap_cols], E.imap_cols, 0.0f, 1.0f, MODE_NEAREST, vv);
@@ -1064,9 +1076,9 @@ inline void env_sample_uv(const RptScene &S, float sx, float sy, float &u, float
       uint32_t row = (uint32_t)(uu * (float)E.imap_rows);
       if (row >= E.imap_rows) row = E.imap_rows - 1;
       cdf_sample(&S.imap_row_pdf[(size_t)row * E.imap_cols], &S.imap_row_cdf[(size_t)row * E.imap_cols], E.imap_cols, 0.0f, 1.0f, MODE_NEAREST, 1.0f, sx, vv, col_pdf);
-      V3 local_wo = uv_to_direction(uu, vv);
+      V3 local_wo = uv_to_direction_cr(uu, vv);
       V3 nw = mul_vec(*reinterpret_cast<const Mat4 *>(E.rot_forward), local_wo);
-      direction_to_uv(nw, u, v);
+      direction_to_uv_cr(nw, u, v);
       pdf = row_pdf * col_pdf * (2.0f * PI_F * PI_F * std::sin(PI_F * v) + 0.001f) + 0.001f;
       return;
     }

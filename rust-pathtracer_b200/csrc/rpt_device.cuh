@@ -185,23 +185,34 @@ __device__ __forceinline__ float3 random_in_unit_disk(float sx, float sy) {
   float v = sqrtf(sy);
   return f3(c * v, s * v, 0.0f);
 }
-// The uv <-> direction maps evaluate their trigonometry as CORRECTLY ROUNDED f32 (through f64): importance-map samples sit
-// exactly on texel boundaries (nearest-mode CDF inversion returns grid points) and then go through
-// uv -> direction -> rotate -> uv -> texel, so a 1-ulp difference between two libm implementations flips the texel that
-// is read. The reference inherits whatever the platform libm does there; both this file and the oracle pin it to the
-// correctly rounded value. Only the Sun / HDR environment paths pay for the f64 calls.
 __device__ __forceinline__ float3 uv_to_direction(float u, float v) {
+  float st, ct, sp, cp;
+  sincosf((u - 0.5f) * RPT_TAU, &st, &ct);
+  sincosf(v * RPT_PI, &sp, &cp);
+  return f3(sp * ct, sp * st, cp);
+}
+__device__ __forceinline__ void direction_to_uv(float3 d, float &u, float &v) {
+  float theta = atan2f(d.y, d.x);
+  float phi = acosf(d.z);
+  u = theta / 2.0f / RPT_PI + 0.5f;
+  v = phi / RPT_PI;
+}
+// The same maps with their trigonometry evaluated as CORRECTLY ROUNDED f32 (through f64), used by the HDR environment only:
+// importance-map samples sit exactly on texel boundaries (nearest-mode CDF inversion returns grid points) and then go
+// through uv -> direction -> rotate -> uv -> texel, so a 1-ulp difference between two libm implementations flips the texel
+// that is read. The reference inherits whatever the platform libm does there; both this file and the oracle pin it to the
+// correctly rounded value. Out of line: the f64 code must not cost the other paths registers.
+__device__ __noinline__ float3 uv_to_direction_cr(float u, float v) {
   double st, ct, sp, cp;
   sincos((double)((u - 0.5f) * RPT_TAU), &st, &ct);
   sincos((double)(v * RPT_PI), &sp, &cp);
   float fst = (float)st, fct = (float)ct, fsp = (float)sp, fcp = (float)cp;
   return f3(fsp * fct, fsp * fst, fcp);
 }
-__device__ __forceinline__ void direction_to_uv(float3 d, float &u, float &v) {
+__device__ __noinline__ float2 direction_to_uv_cr(float3 d) {
   float theta = (float)atan2((double)d.y, (double)d.x);
   float phi = (float)acos((double)d.z);
-  u = theta / 2.0f / RPT_PI + 0.5f;
-  v = phi / RPT_PI;
+  return make_float2(theta / 2.0f / RPT_PI + 0.5f, phi / RPT_PI);
 }
 __device__ __forceinline__ float power_heuristic(float a, float b) { return (a * a) / (a * a + b * b); }
 __device__ __forceinline__ float power_heuristic_generic(float a, float b) { return a / (a + b); }  // src/lib.rs:114-119
@@ -1063,18 +1074,17 @@ __device__ __forceinline__ bool env_in_sun(const DevScene &S, float u, float v) 
 __device__ __forceinline__ float env_emission(const DevScene &S, float u, float v, float lambda) {  // :56-98
   if (S.env_kind == RPT_ENV_CONSTANT) return curve_eval(S, S.env_curve, lambda) * S.env_strength;
   if (S.env_kind == RPT_ENV_SUN) return env_in_sun(S, u, v) ? curve_eval(S, S.env_curve, lambda) * S.env_strength : 0.0f;
-  float3 nd = xform_vec(S.env_rot_rev, uv_to_direction(u, v));
-  float uu, vv;
-  direction_to_uv(nd, uu, vv);
-  return texstack_eval(S, S.env_texstack, lambda, uu, vv) * S.env_strength;
+  float3 nd = xform_vec(S.env_rot_rev, uv_to_direction_cr(u, v));
+  float2 q = direction_to_uv_cr(nd);
+  return texstack_eval(S, S.env_texstack, lambda, q.x, q.y) * S.env_strength;
 }
 __device__ __forceinline__ float env_pdf_for(const DevScene &S, float u, float v) {  // :198-258
   if (S.env_kind == RPT_ENV_CONSTANT) return 1.0f / (4.0f * RPT_PI);
   if (S.env_kind == RPT_ENV_SUN) return env_in_sun(S, u, v) ? 1.0f / (2.0f * RPT_PI * (1.0f - cosf(S.env_angular_diameter))) : 0.0f;
   if (S.imap_rows == 0) return 1.0f / (4.0f * RPT_PI);
-  float3 nd = xform_vec(S.env_rot_rev, uv_to_direction(u, v));
-  float uu, vv;
-  direction_to_uv(nd, uu, vv);
+  float3 nd = xform_vec(S.env_rot_rev, uv_to_direction_cr(u, v));
+  float2 q = direction_to_uv_cr(nd);
+  float uu = q.x, vv = q.y;
   float m = nearest_curve_eval(S.imap_m_pdf, S.imap_marginal_n, uu);
   uint32_t row = (uint32_t)(clampf(uu, 0.0f, 1.0f - RPT_EPS) * (float)S.imap_rows);
   float r = nearest_curve_eval(S.imap_row_pdf + (size_t)row * S.imap_cols, S.imap_cols, vv);
@@ -1100,7 +1110,9 @@ __device__ __forceinline__ void env_sample_uv(const DevScene &S, float sx, float
   uint32_t row = (uint32_t)(uu * (float)S.imap_rows);
   if (row >= S.imap_rows) row = S.imap_rows - 1;
   nearest_cdf_sample(S.imap_row_pdf + (size_t)row * S.imap_cols, S.imap_row_cdf + (size_t)row * S.imap_cols, S.imap_cols, 1.0f, sx, vv, col_pdf);
-  float3 nw = xform_vec(S.env_rot_fwd, uv_to_direction(uu, vv));
-  direction_to_uv(nw, u, v);
+  float3 nw = xform_vec(S.env_rot_fwd, uv_to_direction_cr(uu, vv));
+  float2 q = direction_to_uv_cr(nw);
+  u = q.x;
+  v = q.y;
   pdf = row_pdf * col_pdf * (2.0f * RPT_PI * RPT_PI * sinf(RPT_PI * v) + 0.001f) + 0.001f;
 }
