@@ -577,7 +577,14 @@ struct Trav {
   // inner loop instead of drifting apart iteration by iteration.
   template <bool ANY_HIT>
   __device__ __forceinline__ void run(const DevScene &S, int *stack, int stride, TraceWork &work) {
-    while (true) {
+    while (!step<ANY_HIT>(S, stack, stride, work)) {
+    }
+  }
+  // One iteration of the outer loop: descend to the next leaf, process it, fetch the next node ref.
+  // Returns true when the ray is finished (nothing left to visit, or ANY_HIT accepted a hit).
+  template <bool ANY_HIT>
+  __device__ __forceinline__ bool step(const DevScene &S, int *stack, int stride, TraceWork &work) {
+    {
       // ---- phase 1: descend through inner nodes (inner refs are >= 0)
       while (cur >= 0) {
         work.nodes++;
@@ -598,7 +605,7 @@ struct Trav {
           cur = pop(stack, stride);
         }
       }
-      if (cur == RPT_DONE) return;
+      if (cur == RPT_DONE) return true;
 
       // ---- phase 2: a leaf
       uint32_t idx = (uint32_t)(~cur);
@@ -646,7 +653,7 @@ struct Trav {
               hit = sphere_test(I, lo, ld, 0.0f, closest, tmax, t);
             else
               hit = disk_test(I, lo, ld, 0.0f, closest, tmax, t);
-            if (hit && accept(t, tie_key(kind == RPT_AGG_SPHERE, inst_order, 0), hit_inst, 0) && ANY_HIT) return;
+            if (hit && accept(t, tie_key(kind == RPT_AGG_SPHERE, inst_order, 0), hit_inst, 0) && ANY_HIT) return true;
           }
         }
       }
@@ -657,10 +664,10 @@ struct Trav {
         float t, b0, b1, b2;
         if (tri_test_pre(f3(v0), f3(v1), f3(v2), ro, tr, 0.0f, closest, t, b0, b1, b2) &&
             accept(t, tie_key(false, inst_order, __float_as_uint(v1.w)), hit_inst, tri_local) && ANY_HIT)
-          return;
+          return true;
       }
       cur = have_next ? next : pop(stack, stride);
-      if (cur == RPT_DONE) return;
+      return cur == RPT_DONE;
     }
   }
 };
