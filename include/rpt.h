@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RPT_ABI_VERSION 6u
+#define RPT_ABI_VERSION 7u
 
 /* ---- MaterialId (reference src/materials/mod.rs:22-27) --------------------------
  * Packed as (tag << 16) | table_index; RPT_MAT_NONE = "no override / no id". */
@@ -132,14 +132,18 @@ typedef struct RptEnvironment {
   float imap_marginal_integral;   /* CurveWithCDF.pdf_integral of the marginal */
 } RptEnvironment;
 
-/* ---- Camera (reference src/camera/projective_camera.rs:8-24) --------------------- */
+/* ---- Camera (reference src/camera/projective_camera.rs:8-24, panorama_camera.rs:6-16) -------- */
+enum RptCameraKind { RPT_CAMERA_PROJECTIVE = 0, RPT_CAMERA_PANORAMA = 1 };
+
 typedef struct RptCamera {
   float origin[3];
-  float u[3], v[3], w[3];
-  float lower_left[3];
+  float u[3], v[3], w[3]; /* projective: w = -direction (projective_camera.rs:44-48); panorama: w = +direction (:31-33) */
+  float lower_left[3];    /* projective only */
   float horizontal[3];
   float vertical[3];
-  float aperture_diameter;
+  float aperture_diameter; /* projective only; the panorama camera is a pinhole (panorama_camera.rs:69-73) */
+  uint32_t kind;           /* RptCameraKind */
+  float angle_span[2];     /* panorama: horizontal / vertical field of view in radians (panorama_camera.rs:35-38) */
 } RptCamera;
 
 /* ---- Scene: the flattened World (reference src/world/mod.rs:18-28) -------------- */

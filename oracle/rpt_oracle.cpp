@@ -1088,6 +1088,12 @@ inline void env_sample_uv(const RptScene &S, float sx, float sy, float &u, float
 // ---- camera (camera/projective_camera.rs:101-120) -----------------------------------------------------
 inline V3 a3(const float *p) { return v3(p[0], p[1], p[2]); }
 inline Ray camera_get_ray(const RptCamera &C, float lens_x, float lens_y, float s, float t) {
+  if (C.kind == RPT_CAMERA_PANORAMA) {  // camera/panorama_camera.rs:68-91; `transform.to_world(vec)` = u*x + v*y + w*z (math crate, unpinned)
+    float ax = C.angle_span[0] * (s - 0.5f), ay = C.angle_span[1] * (0.5f - t);
+    float sx = std::sin(ax), cx = std::cos(ax), sy = std::sin(ay), cy = std::cos(ay);
+    V3 vec = v3(sx * cy, sy, cx * cy);
+    return Ray{a3(C.origin), a3(C.u) * vec.x + a3(C.v) * vec.y + a3(C.w) * vec.z, INF_F};
+  }
   V3 vec = random_in_unit_disk(lens_x, lens_y);  // optics::CircularAperture::sample (unpinned)
   V3 rd = C.aperture_diameter * vec;
   V3 offset = a3(C.u) * rd.x + a3(C.v) * rd.y;

@@ -71,7 +71,7 @@ def save_world(path: str, world: W.World, settings: dict, lambda_lo: float, lamb
         "cameras": [
             dict(name=c.name, origin=c.origin.tolist(), u=c.u.tolist(), v=c.v.tolist(), w=c.w.tolist(), lower_left=c.lower_left.tolist(),
                  horizontal=c.horizontal.tolist(), vertical=c.vertical.tolist(), aperture_diameter=c.aperture_diameter, vfov=c.vfov,
-                 focal_distance=c.focal_distance)
+                 focal_distance=c.focal_distance, kind=c.kind, angle_span=[float(c.angle_span[0]), float(c.angle_span[1])])
             for c in world.cameras
         ],
         "camera_names_to_index": world.camera_names_to_index,
@@ -123,6 +123,7 @@ def load_world(path: str) -> Tuple[W.World, dict, Tuple[float, float, int]]:
     for d in meta["cameras"]:
         a = lambda k: np.asarray(d[k], dtype=F32)
         world.cameras.append(W.Camera(d["name"], a("origin"), a("u"), a("v"), a("w"), a("lower_left"), a("horizontal"), a("vertical"),
-                                      d["aperture_diameter"], d["vfov"], d["focal_distance"]))
+                                      d["aperture_diameter"], d["vfov"], d["focal_distance"], kind=d.get("kind", 0),
+                                      angle_span=tuple(d.get("angle_span", (0.0, 0.0)))))
     world.camera_names_to_index = meta["camera_names_to_index"]
     return world, meta["settings"], (lo, hi, n)

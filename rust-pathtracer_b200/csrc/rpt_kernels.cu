@@ -253,15 +253,27 @@ __global__ void __launch_bounds__(256) k_raygen(DevScene S, RenderCtx R, PathRec
     float cu = ((float)px + s0.x) / (float)R.width, cv = ((float)py + s0.y) / (float)R.height;
     float lambda = R.lambda_lo + s0.z * (R.lambda_hi - R.lambda_lo);
     float fu = clampf(cu, 0.0f, 1.0f - RPT_EPS), fv = clampf(cv, 0.0f, 1.0f - RPT_EPS);
-    // ProjectiveCamera::get_ray (camera/projective_camera.rs:101-120)
-    float3 vec = random_in_unit_disk(s1.x, s1.y);
-    float3 rd = R.cam.aperture_diameter * vec;
+    float3 origin, dir;
     float3 cu3 = f3(R.cam.u[0], R.cam.u[1], R.cam.u[2]), cv3 = f3(R.cam.v[0], R.cam.v[1], R.cam.v[2]);
-    float3 origin = f3(R.cam.origin[0], R.cam.origin[1], R.cam.origin[2]) + (cu3 * rd.x + cv3 * rd.y);
-    float3 pop = f3(R.cam.lower_left[0], R.cam.lower_left[1], R.cam.lower_left[2]) +
-                 fu * f3(R.cam.horizontal[0], R.cam.horizontal[1], R.cam.horizontal[2]) +
-                 fv * f3(R.cam.vertical[0], R.cam.vertical[1], R.cam.vertical[2]);
-    float3 dir = normalized(pop - origin);
+    if (R.cam.kind == RPT_CAMERA_PANORAMA) {
+      // PanoramaCamera::get_ray (camera/panorama_camera.rs:68-91): pinhole, direction from azimuth / elevation; not renormalised
+      float ax = R.cam.angle_span[0] * (fu - 0.5f), ay = R.cam.angle_span[1] * (0.5f - fv);
+      float sx, cx, sy, cy;
+      sincosf(ax, &sx, &cx);
+      sincosf(ay, &sy, &cy);
+      float3 vec = f3(sx * cy, sy, cx * cy);
+      origin = f3(R.cam.origin[0], R.cam.origin[1], R.cam.origin[2]);
+      dir = cu3 * vec.x + cv3 * vec.y + f3(R.cam.w[0], R.cam.w[1], R.cam.w[2]) * vec.z;
+    } else {
+      // ProjectiveCamera::get_ray (camera/projective_camera.rs:101-120)
+      float3 vec = random_in_unit_disk(s1.x, s1.y);
+      float3 rd = R.cam.aperture_diameter * vec;
+      origin = f3(R.cam.origin[0], R.cam.origin[1], R.cam.origin[2]) + (cu3 * rd.x + cv3 * rd.y);
+      float3 pop = f3(R.cam.lower_left[0], R.cam.lower_left[1], R.cam.lower_left[2]) +
+                   fu * f3(R.cam.horizontal[0], R.cam.horizontal[1], R.cam.horizontal[2]) +
+                   fv * f3(R.cam.vertical[0], R.cam.vertical[1], R.cam.vertical[2]);
+      dir = normalized(pop - origin);
+    }
     PathRec r;
     r.r0 = make_float4(origin.x, origin.y, origin.z, 1.0f);
     r.r1 = make_float4(dir.x, dir.y, dir.z, 100.0f);

@@ -17,7 +17,7 @@ from . import curves as C
 from . import world as W
 
 F32 = np.float32
-ABI_VERSION = 6
+ABI_VERSION = 7
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "librpt_b200.so")
@@ -71,7 +71,7 @@ class RptEnvironment(ct.Structure):
 class RptCamera(ct.Structure):
     _fields_ = [
         ("origin", c_f * 3), ("u", c_f * 3), ("v", c_f * 3), ("w", c_f * 3), ("lower_left", c_f * 3),
-        ("horizontal", c_f * 3), ("vertical", c_f * 3), ("aperture_diameter", c_f),
+        ("horizontal", c_f * 3), ("vertical", c_f * 3), ("aperture_diameter", c_f), ("kind", c_u32), ("angle_span", c_f * 2),
     ]
 
 
@@ -325,6 +325,8 @@ class FlatScene:
             for name in ("origin", "u", "v", "w", "lower_left", "horizontal", "vertical"):
                 setattr(r, name, _arr(np.asarray(getattr(c, name), dtype=F32).tolist(), c_f, 3))
             r.aperture_diameter = c.aperture_diameter
+            r.kind = c.kind
+            r.angle_span = _arr([float(c.angle_span[0]), float(c.angle_span[1])], c_f, 2)
         k.append(cams)
         d.num_cameras, d.cameras = len(world.cameras), cams
         self.desc = d

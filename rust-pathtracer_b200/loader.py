@@ -554,10 +554,13 @@ def construct_world(config: Config, scene_file: Optional[str] = None, resolver: 
     # -- cameras (parsing/cameras.rs:116-204): one aspect-corrected camera per render setting
     by_name = {}
     for cam in scene["cameras"]:
-        if cam["type"] != "SimpleCamera":
-            continue  # Panorama / Realistic cameras are out of scope
+        if cam["type"] not in ("SimpleCamera", "PanoramaCamera"):
+            continue  # RealisticCamera sits behind a cargo feature (parsing/cameras.rs:101-102): out of scope
         v_up = np.asarray(cam.get("v_up") or [0.0, 0.0, 1.0], dtype=F32)
         v_up = v_up / F32(np.sqrt(np.sum(v_up * v_up, dtype=F32)))
+        if cam["type"] == "PanoramaCamera":  # parsing/cameras.rs:150-160
+            by_name[cam["name"]] = W.Camera.new_panorama(cam["name"], cam["look_from"], cam["look_at"], v_up, cam["fov"][0], cam["fov"][1])
+            continue
         by_name[cam["name"]] = W.Camera.new(
             cam["name"], cam["look_from"], cam["look_at"], v_up, cam["vfov"],
             cam.get("focal_distance") if cam.get("focal_distance") is not None else 10.0,

@@ -174,7 +174,8 @@ class Environment:
 
 @dataclass
 class Camera:
-    """ProjectiveCamera constants (reference src/camera/projective_camera.rs:27-94,121-133)."""
+    """ProjectiveCamera constants (reference src/camera/projective_camera.rs:27-94,121-133); kind 1 = PanoramaCamera
+    (src/camera/panorama_camera.rs:18-62): origin, frame (u, v, w = +direction) and the angle spans in radians."""
 
     name: str
     origin: np.ndarray
@@ -187,6 +188,25 @@ class Camera:
     aperture_diameter: float
     vfov: float
     focal_distance: float
+    kind: int = 0
+    angle_span: Tuple[float, float] = (0.0, 0.0)
+
+    @staticmethod
+    def new_panorama(name, look_from, look_at, v_up, horizontal_fov, vertical_fov) -> "Camera":
+        """PanoramaCamera::new (panorama_camera.rs:18-62); fovs in degrees, clamped to (2 pi, pi)."""
+        f = lambda a: np.asarray(a, dtype=F32)
+        look_from, look_at, v_up = f(look_from), f(look_at), f(v_up)
+
+        def normalized(a):
+            return (a / F32(np.sqrt(np.sum(a * a, dtype=F32)))).astype(F32)
+
+        w = normalized(look_at - look_from)
+        u = normalized(np.cross(v_up, w).astype(F32))
+        v = normalized(np.cross(w, u).astype(F32))
+        hf = float(np.clip(F32(np.deg2rad(F32(horizontal_fov))), F32(0.0), F32(2.0 * np.pi)))
+        vf = float(np.clip(F32(np.deg2rad(F32(vertical_fov))), F32(0.0), F32(np.pi)))
+        z = f([0, 0, 0])
+        return Camera(name, look_from, u, v, w, z, z, z, 0.0, 0.0, 0.0, kind=1, angle_span=(hf, vf))
 
     @staticmethod
     def new(name, look_from, look_at, v_up, vfov, focal_distance, aperture_diameter) -> "Camera":
@@ -204,6 +224,8 @@ class Camera:
         return cam.with_aspect_ratio(1.0)
 
     def with_aspect_ratio(self, aspect: float) -> "Camera":
+        if self.kind == 1:
+            return self  # panorama_camera.rs:92-94
         theta = F32(np.deg2rad(F32(self.vfov)))
         half_height = F32(np.tan(theta / F32(2.0)))
         half_width = F32(aspect) * half_height

@@ -181,6 +181,30 @@ def test_public_api_render(pkg):
     os_.close()
 
 
+@pytest.mark.parametrize("name", ["kitchen_sink", "cornell"])
+def test_panorama_camera(pkg, name):
+    """PanoramaCamera (N4; panorama_camera.rs:68-91) in k_raygen: primary hit ids and the same-stream image against the oracle."""
+    import parity
+
+    world, st, flat = parity.load_scene(name, 128, 64, 8)
+    look_from, look_at = ((0.0, -0.5, 1.0), (1.0, 0.2, 0.2)) if name == "kitchen_sink" else ((0.278, 0.273, 0.3), (0.278, 0.273, 0.0))
+    world.cameras = [pkg.world.Camera.new_panorama("pano", look_from, look_at, (0.0, 0.0, 1.0) if name == "kitchen_sink" else (0.0, 1.0, 0.0), 360.0, 170.0)]
+    flat = pkg.ffi.FlatScene(world, st.wavelength_bounds[0], st.wavelength_bounds[1], 1024)
+    cs, os_ = parity.cuda_scene(flat), parity.oracle_scene(flat)
+    p = st.params(seed=8)
+    gi, gp, gt = cs.trace_primary(p)
+    oi, op, ot = os_.trace_primary(p)
+    assert np.mean((gi == oi) & (gp == op)) >= 0.9999
+    assert len(np.unique(oi)) >= 3
+    fg, cg = cs.render_pt(p)
+    fo, co = os_.render_pt(p)
+    assert np.isfinite(fg).all()
+    assert parity.rel_mse(fg, fo) < 2e-3 and parity.mean_rel_diff(fg, fo) < 2e-3
+    assert cg.camera_rays == co.camera_rays and abs(cg.segments - co.segments) <= max(4, 2e-3 * co.segments)
+    cs.close()
+    os_.close()
+
+
 def test_importance_map_bake_on_device(pkg):
     """N3: rpt_scene_bake_importance_map from the scene's resident environment texels == the oracle's scalar restatement,
     bit for bit (same f32 operation order, no FMA contraction), for the map size of hdri_test.toml and an odd one; the

@@ -285,6 +285,13 @@ aperture_diameter = 0.05
 aperture = { type = "Circular" }
 focal_distance = 6.5
 vfov = 50.0
+
+[[cameras]]
+type = "PanoramaCamera"
+name = "pano"
+look_from = [0.0, -0.5, 1.0]
+look_at = [1.0, 0.2, 0.2]
+fov = [360.0, 160.0]
 """)
     # instanced monkeys (C5): 48 x 50 grid (minus 12) = 2388 instances, Philox-free numpy RNG seed 5
     rng = np.random.default_rng(5)
