@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1041,22 +1042,65 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32
 enum KernelId { K_RAYGEN, K_TRACE, K_SHADE_MISS, K_SHADE_DIFFUSE, K_SHADE_GGX, K_SHADOW, K_FILM, K_NUM };
 const char *kKernelNames[K_NUM] = {"k_raygen", "k_trace", "k_shade_miss", "k_shade_surface<diffuse>", "k_shade_surface<ggx>", "k_shadow", "k_film"};
 
+// Scene arrays are sub-allocated from one device block (small scenes: a single 4 MB block that is handed from scene to
+// scene through a per-device spare, so a create / render / destroy frame loop issues no cudaMalloc / cudaFree for them:
+// each of those costs 0.1-8 ms and cudaFree synchronises the device). Arrays larger than 1 MB get their own allocation.
 struct DeviceBuffers {
-  std::vector<void *> ptrs;
+  static constexpr size_t kBlock = (size_t)4 << 20;
+  std::vector<void *> ptrs;  // every cudaMalloc'd block this scene owns
+  char *block = nullptr;
+  size_t block_size = 0, block_used = 0;
+  int device = 0;
+  static void *&spare(int device) {
+    static void *s[64] = {nullptr};
+    return s[device & 63];
+  }
+  int reserve(size_t bytes, void **out) {
+    *out = nullptr;
+    if (bytes > ((size_t)1 << 20)) {
+      CUDA_TRY(cudaMalloc(out, bytes));
+      ptrs.push_back(*out);
+      return 0;
+    }
+    size_t at = (block_used + 255) & ~(size_t)255;
+    if (!block || at + bytes > block_size) {
+      void *p = spare(device);
+      if (p) {
+        spare(device) = nullptr;
+      } else {
+        CUDA_TRY(cudaMalloc(&p, kBlock));
+      }
+      ptrs.push_back(p);
+      block = static_cast<char *>(p);
+      block_size = kBlock;
+      at = 0;
+    }
+    *out = block + at;
+    block_used = at + bytes;
+    return 0;
+  }
   template <class T>
   int upload(const T *host, size_t n, const T **out) {
     *out = nullptr;
     if (n == 0) return 0;
     void *p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
-    ptrs.push_back(p);
+    if (int rc = reserve(n * sizeof(T), &p)) return rc;
     CUDA_TRY(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
     *out = static_cast<const T *>(p);
     return 0;
   }
   void release() {
-    for (void *p : ptrs) cudaFree(p);
+    for (void *p : ptrs) {
+      if (!p) continue;
+      if (p == block && block_size == kBlock && !spare(device)) {
+        spare(device) = p;  // keep one standard block per device for the next scene
+        continue;
+      }
+      cudaFree(p);
+    }
     ptrs.clear();
+    block = nullptr;
+    block_size = block_used = 0;
   }
 };
 
@@ -1151,6 +1195,8 @@ struct WaveCache {
   WaveBuffers wave{};
   size_t slots = 0, shadow = 0, acc = 0;
   bool valid = false;
+  float4 *film = nullptr;  // one parked film buffer (same reason: no cudaMalloc / cudaFree in a steady frame loop)
+  size_t film_pixels = 0;
 };
 WaveCache g_wave_cache[64];
 
@@ -1207,12 +1253,15 @@ int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid) {
       S->wave_slots = c.slots;
       S->wave_shadow = c.shadow;
       S->wave_acc = c.acc;
-      c = WaveCache{};
+      c.wave = WaveBuffers{};
+      c.slots = c.shadow = c.acc = 0;
+      c.valid = false;
       return 0;
     }
     if (c.valid) {  // too small for this job: release it before allocating a bigger set
       release_wave_buffers(c.wave);
-      c = WaveCache{};
+      c.slots = c.shadow = c.acc = 0;
+      c.valid = false;
     }
   }
   WaveBuffers &w = S->wave;
@@ -1299,7 +1348,14 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   if (S->film_pixels != wh) {
     if (S->film) cudaFree(S->film);
     S->film = nullptr;
-    CUDA_TRY(cudaMalloc(&S->film, wh * sizeof(float4)));
+    WaveCache &fc = g_wave_cache[S->device & 63];
+    if (fc.film && fc.film_pixels == wh) {
+      S->film = fc.film;
+      fc.film = nullptr;
+      fc.film_pixels = 0;
+    } else {
+      CUDA_TRY(cudaMalloc(&S->film, wh * sizeof(float4)));
+    }
     S->film_pixels = wh;
   }
   CUDA_TRY(cudaMemsetAsync(S->film, 0, wh * sizeof(float4), S->stream));
@@ -1439,7 +1495,15 @@ int rpt_scene_destroy(RptScene *S) {
   if (!S) return 0;
   cudaSetDevice(S->device);
   park_wave(S);
-  if (S->film) cudaFree(S->film);
+  if (S->film) {
+    WaveCache &fc = g_wave_cache[S->device & 63];
+    if (!fc.film) {
+      fc.film = S->film;
+      fc.film_pixels = S->film_pixels;
+    } else {
+      cudaFree(S->film);
+    }
+  }
   S->bufs.release();
   for (cudaEvent_t e : S->ev_pool) cudaEventDestroy(e);
   if (S->stream) cudaStreamDestroy(S->stream);
@@ -1456,16 +1520,26 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail("no such CUDA device (there is no CPU fallback)");
   CUDA_TRY(cudaSetDevice(device));
+  const bool timing = std::getenv("RPT_TIMING") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[rpt_scene_create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+    t_start = now;
+  };
   RptScene *S = new RptScene();
   S->device = device;
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  S->num_sms = prop.multiProcessorCount;
+  S->bufs.device = device;
+  // (cudaGetDeviceProperties costs 2.5-2.8 ms per call on this driver: it was 90 % of scene creation)
+  CUDA_TRY(cudaDeviceGetAttribute(&S->num_sms, cudaDevAttrMultiProcessorCount, device));
   auto bail = [&](int rc) {
     rpt_scene_destroy(S);
     return rc;
   };
+  lap("device properties");
   if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
+  lap("stream create");
 
   // ---- geometry: per-mesh BLAS, then the TLAS over instance boxes
   std::vector<DevNode> nodes;
@@ -1667,6 +1741,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     light_geom_box.insert(light_geom_box.end(), ibox[i].mx, ibox[i].mx + 3);
   }
 
+  lap("host BVH build + flatten");
   DevScene &D = S->dev;
   DeviceBuffers &B = S->bufs;
   int rc = 0;
@@ -1742,6 +1817,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   S->stats.scene_bytes_total = S->stats.node_bytes + S->stats.triangle_bytes + insts.size() * sizeof(DevInstance) +
                                (size_t)d->num_curves * d->num_lambda * 4 + tex_bytes;
 
+  lap("uploads");
   size_t film_smem = 3 * (size_t)d->num_lambda * sizeof(float);
   if (film_smem > 48 * 1024) {
     if (cudaFuncSetAttribute(k_film, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)film_smem) != cudaSuccess)
@@ -1765,6 +1841,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_surface<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
   S->grid[K_SHADOW] = occupancy_grid(k_shadow, TRACE_THREADS, S->stack_smem, S->num_sms);
   S->grid[K_FILM] = occupancy_grid(k_film, 256, film_smem, S->num_sms);
+  lap("occupancy queries");
   *out = S;
   return 0;
 }

@@ -185,9 +185,11 @@ class CudaRenderer:
         film = device_tensor(ptr, (st.height, st.width, 4), self.device)
         if world_size > 1:
             dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+            # the collective runs on NCCL's stream and only torch's current stream waits for it; the library normalises on
+            # its own stream, so the host has to see the reduce finished first
+            torch.cuda.current_stream(self.device).synchronize()
         if rank == 0:
             scene.film_scale(film.data_ptr(), st.height * st.width, 1.0 / st.min_samples)
-            torch.cuda.synchronize(self.device)
         return film, counters
 
 
