@@ -317,8 +317,17 @@ def main():
         per_launch_bytes = hbm_bytes[dominant] / launches_per_step
         per_launch_ms = ktimes[dominant]["ms"] / ktimes[dominant]["launches"]
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        # measured DRAM traffic of the same kernel on the same workload: the committed ncu launch list (profiles/README.md)
+        traffic, traffic_src, ncu_share = None, None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if args.scene == "cornell" and (args.width, args.height, args.spp) == (None, None, None) and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if dominant in tj.get("kernels", {}):
+                traffic = tj["kernels"][dominant]["dram_bytes_per_launch"]
+                ncu_share = tj["kernels"][dominant]["share"]
+                traffic_src = "profiles/ncu_traffic.json <- " + tj.get("source", "?") + " (dram__bytes_read.sum + dram__bytes_write.sum per launch, same command)"
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
+                    "traffic": traffic, "traffic_source": traffic_src, "ncu_time_share": ncu_share, "peak_source": peak_src, "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                     "launches_per_step": launches_per_step,
                     "bvh_fetch_gbps_cache_level": bvh_bytes.get(dominant, 0) / launches_per_step / (per_launch_ms * 1e-3) / 1e9,
                     "note": "BVH + geometry = %d B, L1-resident: this kernel is bound by instruction issue / L1 latency under divergence, not by HBM; "
