@@ -68,7 +68,9 @@ struct __align__(16) HitRec {
 // chunk tails, see chunk_append); the N_* entries count valid items and feed the Profile counters.
 enum : uint32_t {
   Q_PATHS = 0, Q_MISS = 1, Q_DIFFUSE = 2, Q_GGX = 3, Q_SHADOW = 4, Q_NAN = 5, Q_SHADOW_REF = 6,
-  N_PATHS = 7, N_MISS = 8, N_DIFFUSE = 9, N_GGX = 10, N_SHADOW = 11, Q_COUNT = 12
+  N_PATHS = 7, N_MISS = 8, N_DIFFUSE = 9, N_GGX = 10, N_SHADOW = 11,
+  F_TRACE = 12, F_SHADOW = 13, F_SHADE_DIFFUSE = 14, F_SHADE_GGX = 15,  // claim counters of the dynamic tile hand-out (TileStream)
+  Q_COUNT = 16
 };
 #define RPT_MAX_BOUNCES 64
 
@@ -219,7 +221,43 @@ __device__ __forceinline__ void flush_count(uint32_t v, uint32_t *dst) {
   if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, v);
 }
 
+// Dynamic hand-out of a queue's tiles (32 consecutive entries each) to warps. Rays cost 1..30 node visits and vertices
+// differ in their NEE work, so with a static split the warps of a launch finish far apart (ncu: achieved occupancy 41 of a
+// possible 50 % in the traversal kernels); here a warp claims `grab` tiles with one atomicAdd and keeps claiming until the
+// queue is empty, so all warps finish together (Cornell: trace 7.4 -> 5.9 ms, shadow 8.3 -> 7.2, shade 8.2 -> 7.3).
+// * grab is sized so that a warp makes about CLAIMS_PER_WARP claims per launch whatever the queue length: the balance
+//   granularity stays a few percent of a warp's share, and the claim counter sees a bounded number of atomics (same-address
+//   atomics sustain ~0.7 G/s; a fixed grab of 2 tiles cost a streaming scene - one sphere, a ray is one node test - 33 ms
+//   of a 27 ms kernel).
+// * the NEXT claim is issued as soon as the current one is taken up, so its latency overlaps the tiles being processed.
+#define CLAIMS_PER_WARP 32u
+struct TileStream {
+  uint32_t *ctr;
+  uint32_t n_tiles, grab, cur, lim, pending;
+  __device__ __forceinline__ uint32_t claim() const { return (threadIdx.x & 31u) == 0 ? atomicAdd(ctr, grab) : 0u; }
+  __device__ __forceinline__ void init(uint32_t *counter, uint32_t n_tiles_, uint32_t total_warps) {
+    ctr = counter;
+    n_tiles = n_tiles_;
+    grab = min(64u, max(1u, n_tiles_ / (total_warps * CLAIMS_PER_WARP)));
+    cur = lim = 0;
+    pending = claim();
+  }
+  // warp-uniform; returns the next tile or RPT_NONE when the queue is exhausted
+  __device__ __forceinline__ uint32_t next() {
+    if (cur < lim) return cur++;
+    const uint32_t base = __shfl_sync(0xFFFFFFFFu, pending, 0);
+    if (base >= n_tiles) return RPT_NONE;  // (pending keeps its value: every later call lands here again)
+    cur = base;
+    lim = min(base + grab, n_tiles);
+    pending = claim();
+    return cur++;
+  }
+};
+
 #define TRACE_THREADS 128
+#ifndef TRACE_DYNAMIC
+#define TRACE_DYNAMIC 1
+#endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 8  // resident CTAs per SM the traversal kernels are compiled for (register cap = 65536 / (128 * this))
 #endif
@@ -329,7 +367,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
   uint32_t stage = 0, phase = 0;  // phase bit k = parity to wait for on stage k
   uint32_t tile0 = blockIdx.x * kWarps + warp;
   if (TMA && tile0 < n_tiles && lane == 0) issue(0, tile0);
-  for (uint32_t tile = tile0; tile < n_tiles; tile += total_warps) {
+  auto body = [&](uint32_t tile) {
     const uint32_t i = tile * 32u + lane;
     bool active = i < n;
     uint32_t cls = RPT_NONE;
@@ -388,6 +426,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
     n_miss += cls == Q_MISS;
     n_diffuse += cls == Q_DIFFUSE;
     n_ggx += cls == Q_GGX;
+  };
+  if (TMA || !TRACE_DYNAMIC) {
+    for (uint32_t tile = tile0; tile < n_tiles; tile += total_warps) body(tile);
+  } else {
+    TileStream ts;
+    ts.init(counts + F_TRACE, n_tiles, total_warps);
+    for (uint32_t tile = ts.next(); tile != RPT_NONE; tile = ts.next()) body(tile);
   }
   if (wc_miss.used < QCHUNK) chunk_pad(wc_miss, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
   if (wc_diffuse.used < QCHUNK) chunk_pad(wc_diffuse, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; });
@@ -431,6 +476,9 @@ __global__ void __launch_bounds__(256) k_shade_miss(DevScene S, const PathRec *_
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 6
 #endif
+#ifndef SHADE_DYNAMIC
+#define SHADE_DYNAMIC 1
+#endif
 template <uint32_t CLASS>
 __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surface(DevScene S, RenderCtx R, uint32_t bounce, const PathRec *__restrict__ paths,
                                                        const HitRec *__restrict__ hits, const uint32_t *__restrict__ queue,
@@ -443,7 +491,6 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
   // 10 warps per issue). [stage][float4 k][thread]: consecutive threads hit consecutive 16-byte words.
   __shared__ float4 s_stage[2][5][SHADE_THREADS];
   const uint32_t n = counts[CLASS];
-  const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t n_round = (n + 31u) & ~31u;
   const uint32_t L = R.light_samples;
   const uint32_t max_bounces = R.only_direct ? 1u : R.max_bounces;
@@ -468,15 +515,35 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
   uint32_t n_next = 0, n_shadow = 0, n_sh_ref = 0, n_nan = 0;
   auto mark_next = [&](uint32_t e) { out[e].r3 = make_float4(__uint_as_float(RPT_NONE), 0.0f, 0.0f, 0.0f); };
   auto mark_shadow = [&](uint32_t e) { sh_c[e] = RPT_NONE; };
-  uint32_t i0 = blockIdx.x * blockDim.x + tid;
-  uint32_t idx_cur = i0 < n ? __ldg(queue + i0) : RPT_NONE;
-  uint32_t idx_next = i0 + stride < n ? __ldg(queue + i0 + stride) : RPT_NONE;
+  // The warp's stream of tiles (32 consecutive queue entries each): claimed from a device counter through TileStream
+  // (or, SHADE_DYNAMIC=0, the static round-robin split), two tiles ahead of the one being shaded so that the cp.async
+  // prefetch pipeline below never drains at a claim boundary.
+  const uint32_t lane = tid & 31u;
+  const uint32_t n_tiles = n_round >> 5;
+#if SHADE_DYNAMIC
+  TileStream ts;
+  ts.init(counts + (CLASS == Q_DIFFUSE ? F_SHADE_DIFFUSE : F_SHADE_GGX), n_tiles, gridDim.x * (SHADE_THREADS / 32));
+  auto next_tile = [&]() -> uint32_t { return ts.next(); };
+#else
+  uint32_t g_cur = blockIdx.x * (SHADE_THREADS / 32) + (tid >> 5);
+  auto next_tile = [&]() -> uint32_t {
+    uint32_t t = g_cur;
+    g_cur += gridDim.x * (SHADE_THREADS / 32);
+    return t < n_tiles ? t : RPT_NONE;
+  };
+#endif
+  auto tile_idx = [&](uint32_t t) -> uint32_t {
+    uint32_t i = t * 32u + lane;
+    return (t != RPT_NONE && i < n) ? __ldg(queue + i) : RPT_NONE;
+  };
+  uint32_t t_cur = next_tile(), t_next = next_tile();
+  uint32_t idx_cur = tile_idx(t_cur), idx_next = tile_idx(t_next);
   issue(0, idx_cur);
   int stage = 0;
-  for (uint32_t i = i0; i < n_round; i += stride) {
+  while (t_cur != RPT_NONE) {
     issue(stage ^ 1, idx_next);  // prefetch the next item while this one is shaded
-    uint32_t i_nn = i + 2 * stride;
-    uint32_t idx_nn = i_nn < n ? __ldg(queue + i_nn) : RPT_NONE;
+    uint32_t t_nn = next_tile();
+    uint32_t idx_nn = tile_idx(t_nn);
     cp_async_wait<1>();  // everything but the group just committed has landed
     bool active = idx_cur != RPT_NONE;  // beyond the queue, or chunk padding
     bool continues = false, do_nee = false;
@@ -660,6 +727,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
     stage ^= 1;
     idx_cur = idx_next;
     idx_next = idx_nn;
+    t_cur = t_next;
+    t_next = t_nn;
   }
   cp_async_wait<0>();
   if (wc_next.used < QCHUNK) chunk_pad(wc_next, mark_next);
@@ -673,15 +742,17 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
 // NEE visibility. Light samples: closest hit, accepted when ANY light-material surface is hit, whose own
 // emission is used (pt.rs:177-218, F9). Environment samples: any hit kills the sample (pt.rs:254-263).
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
-                                                          const uint32_t *__restrict__ sh_c, const uint32_t *__restrict__ counts,
+                                                          const uint32_t *__restrict__ sh_c, uint32_t *__restrict__ counts,
                                                           float *__restrict__ acc, unsigned long long *__restrict__ work) {
   extern __shared__ int s_stack[];
   TraceWork tw{0, 0, 0};
   const uint32_t n = counts[Q_SHADOW];
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n_tiles = (n + 31u) >> 5;
+  auto body = [&](uint32_t i) {
+    if (i >= n) return;
     uint32_t c = __ldg(sh_c + i);
-    if (c == RPT_NONE) continue;  // chunk padding
+    if (c == RPT_NONE) return;  // chunk padding
     float4 a = __ldg(sh_a + i), b = __ldg(sh_b + i);
     float3 o = f3(a), d = f3(b);
     float pre = a.w, lambda = b.w;
@@ -689,7 +760,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
     TraceHit th;
     if (c & 0x80000000u) {
       if (!trace_ray<true>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) atomicAdd(acc + slot, pre);
-      continue;
+      return;
     }
     bool lit;
     if (S.num_light_geom) {
@@ -733,7 +804,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
           }
         }
       }
-      if (!found_l) continue;  // no light along the ray: nothing to add
+      if (!found_l) return;  // no light along the ray: nothing to add
       Trav tv;
       tv.init(S, o, d, RPT_INF);
       tv.closest = tl;  // only geometry that beats the light (closer, or equal t with a winning tie key) is accepted
@@ -761,6 +832,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
         if (v != 0.0f) atomicAdd(acc + slot, v);
       }
     }
+  };
+  if (!TRACE_DYNAMIC) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) body(i);
+  } else {
+    TileStream ts;
+    ts.init(counts + F_SHADOW, n_tiles, gridDim.x * (TRACE_THREADS / 32));
+    for (uint32_t tile = ts.next(); tile != RPT_NONE; tile = ts.next()) body(tile * 32u + lane);
   }
   flush_work(tw, work);
 }
