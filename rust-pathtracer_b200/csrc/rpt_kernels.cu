@@ -2,7 +2,7 @@
 //
 // Pipeline per wave of N = width*height*spp_chunk camera samples (reference pt.rs:397-615 unrolled
 // into a bounce-synchronous wavefront):
-//   k_raygen            : film jitter, wavelength, thin-lens camera ray            -> path queue
+//   k_raygen            : film jitter, wavelength, camera ray -> path queue (fused into bounce 0 of k_trace in a render)
 //   per bounce b:
 //     k_trace           : two-level BVH closest hit, sorts paths by material class  -> hit records + class lists
 //     k_shade_miss      : environment vertex: emission * MIS                         (pt.rs:487-511)
@@ -281,9 +281,8 @@ __device__ __forceinline__ void flush_work(const TraceWork &w, unsigned long lon
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_raygen(DevScene S, RenderCtx R, PathRec *__restrict__ out, uint32_t *__restrict__ counts) {
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < R.n_slots; slot += stride) {
+// The camera vertex of sample `slot` (pt.rs:397-446): film jitter, wavelength, camera ray.
+__device__ __forceinline__ PathRec camera_record(const RenderCtx &R, uint32_t slot) {
     uint32_t pixel = slot % R.wh, sample = R.sample_base + slot / R.wh;
     uint32_t px = pixel % R.width, py = pixel / R.width;
     RptRand4 s0 = rpt_philox(R.seed, pixel, sample, 0);
@@ -318,8 +317,12 @@ __global__ void __launch_bounds__(256) k_raygen(DevScene S, RenderCtx R, PathRec
     r.r1 = make_float4(dir.x, dir.y, dir.z, 100.0f);
     r.r2 = make_float4(dir.x, dir.y, dir.z, lambda);
     r.r3 = make_float4(__uint_as_float(slot), 0.0f, 0.0f, 0.0f);
-    out[slot] = r;
-  }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_raygen(DevScene S, RenderCtx R, PathRec *__restrict__ out, uint32_t *__restrict__ counts) {
+  uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < R.n_slots; slot += stride) out[slot] = camera_record(R, slot);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     counts[Q_PATHS] = R.n_slots;
     counts[N_PATHS] = R.n_slots;
@@ -331,11 +334,15 @@ __device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t m
 }
 
 // Closest-hit traversal of the path queue; appends each path to the list of its vertex's class.
-template <bool TMA>
+// RAYGEN: the launch of bounce 0 generates its camera vertices itself (and writes them out for the shade kernel) instead
+// of reading what a separate ray-generation kernel wrote: one 64-byte queue write + read per sample less.
+template <bool TMA, bool RAYGEN = false>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
                                                          uint32_t *__restrict__ q_miss, uint32_t *__restrict__ q_diffuse,
                                                          uint32_t *__restrict__ q_ggx, uint32_t *__restrict__ counts,
-                                                         unsigned long long *__restrict__ work) {
+                                                         unsigned long long *__restrict__ work, RenderCtx R = RenderCtx{},
+                                                         PathRec *__restrict__ paths_out = nullptr) {
+  static_assert(!(TMA && RAYGEN), "the fused ray generation has no input queue to stage");
   extern __shared__ int s_stack[];  // [stack entry][thread]; depth chosen per scene at rpt_scene_create
   // Queue read, two selectable forms (rpt_scene_create picks one; RPT_TMA_TILES=1 selects the TMA form):
   //  * TMA-staged tiles: each warp owns two 2 KB buffers (32 path records each) and two mbarriers. Lane 0 arms the
@@ -356,7 +363,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
   TraceWork tw{0, 0, 0};
   WarpChunk wc_miss = chunk_init(), wc_diffuse = chunk_init(), wc_ggx = chunk_init();
   uint32_t n_miss = 0, n_diffuse = 0, n_ggx = 0;
-  const uint32_t n = counts[Q_PATHS];
+  const uint32_t n = RAYGEN ? R.n_slots : counts[Q_PATHS];
+  if (RAYGEN && blockIdx.x == 0 && threadIdx.x == 0) {
+    counts[Q_PATHS] = n;
+    counts[N_PATHS] = n;
+  }
   const uint32_t n_tiles = (n + 31u) >> 5;
   const uint32_t total_warps = gridDim.x * kWarps;
   auto issue = [&](uint32_t stage, uint32_t tile) {
@@ -386,6 +397,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
       }
       __syncwarp();  // every lane holds its record in registers: the buffer may be refilled
       stage ^= 1u;
+    } else if (RAYGEN) {
+      if (active) {
+        r = camera_record(R, i);
+        paths_out[i] = r;
+      }
     } else if (active) {
       const float4 *rp = reinterpret_cast<const float4 *>(paths + i);
       r.r0 = __ldg(rp);
@@ -1482,15 +1498,20 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
     R.sample_base = P->spp_offset + done;
     CUDA_TRY(cudaMemsetAsync(w.counts, 0, h_counts.size() * sizeof(uint32_t), S->stream));
     CUDA_TRY(cudaMemsetAsync(w.acc, 0, (size_t)R.n_slots * sizeof(float), S->stream));
-    T.begin(K_RAYGEN);
-    k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
-    T.end();
+    const bool fused_raygen = !S->tma_tiles;  // bounce 0's k_trace generates the camera vertices itself
+    if (!fused_raygen) {
+      T.begin(K_RAYGEN);
+      k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
+      T.end();
+    }
     for (uint32_t b = 0; b < max_bounces; ++b) {
       uint32_t *cb = w.counts + (size_t)b * Q_COUNT, *cn = w.counts + (size_t)(b + 1) * Q_COUNT;
       PathRec *in = w.paths[b & 1], *out = w.paths[(b + 1) & 1];
       T.begin(K_TRACE);
       if (S->tma_tiles)
         k_trace<true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work);
+      else if (b == 0 && fused_raygen)
+        k_trace<false, true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, nullptr, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, R, in);
       else
         k_trace<false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work);
       T.end();
@@ -1906,6 +1927,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   if (S->stack_smem > 48 * 1024) {
     cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
     cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
+    cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
     cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
     cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
   }
