@@ -340,8 +340,8 @@ template <bool TMA, bool RAYGEN = false>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
                                                          uint32_t *__restrict__ q_miss, uint32_t *__restrict__ q_diffuse,
                                                          uint32_t *__restrict__ q_ggx, uint32_t *__restrict__ counts,
-                                                         unsigned long long *__restrict__ work, RenderCtx R = RenderCtx{},
-                                                         PathRec *__restrict__ paths_out = nullptr) {
+                                                         unsigned long long *__restrict__ work, float *__restrict__ acc,
+                                                         RenderCtx R = RenderCtx{}, PathRec *__restrict__ paths_out = nullptr) {
   static_assert(!(TMA && RAYGEN), "the fused ray generation has no input queue to stage");
   extern __shared__ int s_stack[];  // [stack entry][thread]; depth chosen per scene at rpt_scene_create
   // Queue read, two selectable forms (rpt_scene_create picks one; RPT_TMA_TILES=1 selects the TMA form):
@@ -421,7 +421,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
       h.pad = 0;
       hits[i] = h;
       if (!hit) {
-        cls = Q_MISS;
+        if (S.env_kind == RPT_ENV_CONSTANT) {
+          // The environment vertex of a direction-independent environment is finished here, from the path record that is
+          // still in registers (same arithmetic as k_shade_miss): no class-list entry, no 64-byte re-gather.
+          float lambda = r.r2.w, beta = r.r0.w, pdf_fwd = r.r1.w;
+          float emission = curve_eval(S, S.env_curve, lambda) * S.env_strength;  // env_emission, Constant
+          float cos_i = fabsf(dot(f3(r.r1), d));
+          float nee_psa_pdf = (1.0f / (4.0f * RPT_PI)) / fabsf(cos_i);  // env_pdf_for, Constant
+          float bsdf_psa_pdf = pdf_fwd / fabsf(cos_i);
+          float c = power_heuristic(bsdf_psa_pdf, nee_psa_pdf) * beta * emission;
+          if (c != 0.0f) atomicAdd(acc + __float_as_uint(r.r3.x), c);
+          n_miss++;
+        } else {
+          cls = Q_MISS;
+        }
       } else {
         const DevInstance &I = S.instances[th.inst];
         uint32_t mat = I.material;
@@ -1509,15 +1522,17 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       PathRec *in = w.paths[b & 1], *out = w.paths[(b + 1) & 1];
       T.begin(K_TRACE);
       if (S->tma_tiles)
-        k_trace<true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work);
+        k_trace<true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc);
       else if (b == 0 && fused_raygen)
-        k_trace<false, true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, nullptr, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, R, in);
+        k_trace<false, true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, nullptr, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc, R, in);
       else
-        k_trace<false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work);
+        k_trace<false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc);
       T.end();
-      T.begin(K_SHADE_MISS);
-      k_shade_miss<<<S->grid[K_SHADE_MISS], 256, 0, S->stream>>>(S->dev, in, w.q_miss, cb, w.acc);
-      T.end();
+      if (S->dev.env_kind != RPT_ENV_CONSTANT) {  // (a Constant environment's vertices are finished inside k_trace)
+        T.begin(K_SHADE_MISS);
+        k_shade_miss<<<S->grid[K_SHADE_MISS], 256, 0, S->stream>>>(S->dev, in, w.q_miss, cb, w.acc);
+        T.end();
+      }
       T.begin(K_SHADE_DIFFUSE);
       k_shade_surface<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
       T.end();
@@ -1988,9 +2003,9 @@ int rpt_trace_primary(RptScene *S, const RptRenderParams *P, uint32_t *inst, uin
   CUDA_TRY(cudaMemsetAsync(w.counts, 0, (RPT_MAX_BOUNCES + 1) * Q_COUNT * sizeof(uint32_t), S->stream));
   k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
   if (S->tma_tiles)
-    k_trace<true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts, w.work);
+    k_trace<true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts, w.work, w.acc);
   else
-    k_trace<false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts, w.work);
+    k_trace<false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts, w.work, w.acc);
   std::vector<HitRec> h(wh);
   CUDA_TRY(cudaMemcpyAsync(h.data(), w.hits, wh * sizeof(HitRec), cudaMemcpyDeviceToHost, S->stream));
   CUDA_TRY(cudaStreamSynchronize(S->stream));
