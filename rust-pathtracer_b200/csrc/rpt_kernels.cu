@@ -1305,6 +1305,10 @@ struct WaveCache {
   bool valid = false;
   float4 *film = nullptr;  // one parked film buffer (same reason: no cudaMalloc / cudaFree in a steady frame loop)
   size_t film_pixels = 0;
+  // one parked stream + timing-event pool: a scene's first render on a brand-new stream with ~100 fresh events stalled the
+  // host for 20-70 ms in one frame out of five (measured, tools/e2e_probe.py), with the device time unchanged
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> events;
 };
 WaveCache g_wave_cache[64];
 
@@ -1620,6 +1624,14 @@ int rpt_scene_destroy(RptScene *S) {
     }
   }
   S->bufs.release();
+  {
+    WaveCache &sc = g_wave_cache[S->device & 63];
+    if (S->stream && !sc.stream) {  // (every entry point leaves the stream idle: nothing is pending on it)
+      sc.stream = S->stream;
+      sc.events.swap(S->ev_pool);
+      S->stream = nullptr;
+    }
+  }
   for (cudaEvent_t e : S->ev_pool) cudaEventDestroy(e);
   if (S->stream) cudaStreamDestroy(S->stream);
   delete S;
@@ -1653,7 +1665,16 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     return rc;
   };
   lap("device properties");
-  if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
+  {
+    WaveCache &sc = g_wave_cache[device & 63];
+    if (sc.stream) {
+      S->stream = sc.stream;
+      S->ev_pool.swap(sc.events);
+      sc.stream = nullptr;
+    } else if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      return bail(fail("cudaStreamCreate failed"));
+    }
+  }
   lap("stream create");
 
   // ---- geometry: per-mesh BLAS, then the TLAS over instance boxes
@@ -1976,9 +1997,15 @@ int rpt_render_pt_device(RptScene *S, const RptRenderParams *P, void **film_dev,
 int rpt_render_pt(RptScene *S, const RptRenderParams *P, float *film_xyzw, RptCounters *counters) {
   if (!film_xyzw) return fail("null argument");
   void *dev = nullptr;
+  const bool timing = std::getenv("RPT_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
   if (int rc = rpt_render_pt_device(S, P, &dev, counters)) return rc;
+  auto t1 = std::chrono::steady_clock::now();
   CUDA_TRY(cudaMemcpyAsync(film_xyzw, dev, S->film_pixels * sizeof(float4), cudaMemcpyDeviceToHost, S->stream));
   CUDA_TRY(cudaStreamSynchronize(S->stream));
+  if (timing)
+    fprintf(stderr, "[rpt_render_pt] render %8.3f ms (device %.3f)  film D2H %8.3f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+            counters ? counters->device_ms : 0.0f, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   return 0;
 }
 
