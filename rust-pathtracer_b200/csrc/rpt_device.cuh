@@ -23,6 +23,12 @@
 #define RPT_NORMAL_OFFSET 0.001f /* reference src/lib.rs:48 */
 #define RPT_NONE 0xFFFFFFFFu
 #define RPT_INF __int_as_float(0x7f800000)
+// BVH work counters (nodes / triangles / instances visited, reported through RptCounters): compiled in unless RPT_NO_TRAV_STATS
+#ifdef RPT_NO_TRAV_STATS
+#define RPT_STAT(x) ((void)0)
+#else
+#define RPT_STAT(x) x
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Device scene (SoA buffers in HBM; pointers passed by value inside DevScene as a kernel param)
@@ -587,7 +593,7 @@ struct Trav {
     {
       // ---- phase 1: descend through inner nodes (inner refs are >= 0)
       while (cur >= 0) {
-        work.nodes++;
+        RPT_STAT(work.nodes++);
         const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
         float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
         int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
@@ -625,7 +631,7 @@ struct Trav {
         } else {
           // TLAS leaf: a whole instance
           is_tri = false;
-          work.insts++;
+          RPT_STAT(work.insts++);
           const DevInstance &I = S.instances[hit_inst];
           uint32_t flags = I.flags;
           float3 lo = o, ld = d;
@@ -658,7 +664,7 @@ struct Trav {
         }
       }
       if (is_tri) {
-        work.tris++;
+        RPT_STAT(work.tris++);
         const float4 *tv = S.tri_verts + 3 * (size_t)tri;
         float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
         float t, b0, b1, b2;

@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
         float t;
         bool hit = kind == RPT_AGG_RECT ? rect_test(I, lo, ld, 0.0f, tl, RPT_INF, t)
                                         : (kind == RPT_AGG_SPHERE ? sphere_test(I, lo, ld, 0.0f, tl, RPT_INF, t) : disk_test(I, lo, ld, 0.0f, tl, RPT_INF, t));
-        tw.insts++;
+        RPT_STAT(tw.insts++);
         if (hit) {
           uint64_t key = tie_key(kind == RPT_AGG_SPHERE, I.order, 0);
           if (!found_l || t < tl || key > key_l) {
