@@ -22,6 +22,7 @@ two un-vendored git crates and cannot be built in this image, so this arm runs t
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -210,6 +211,8 @@ def main():
     sync()
     if sampler:
         sampler.lines.clear()
+    gc.collect()
+    gc.disable()
     t0 = time.perf_counter()
     dev_ms, segs, launches, last_cnt = 0.0, 0, 0, None
     ktimes, pending = {}, []
@@ -226,6 +229,7 @@ def main():
             a["launches"] += k["launches"]
     sync()
     wall = time.perf_counter() - t0
+    gc.enable()
     clocks = sampler.stop() if sampler else None
     dev_ms += sum(e0.elapsed_time(e1) for e0, e1 in pending)
 
@@ -246,7 +250,7 @@ def main():
     # ---- e2e through the public API with host buffers (scene upload + render + film D2H, every step)
     renderer = pkg.CudaRenderer(device=local_rank)
     pinned = torch.empty((st.height, st.width, 4), dtype=torch.float32).pin_memory()
-    e2e_steps = max(2, min(K, 10))
+    e2e_steps = max(2, min(3 * K, 30))  # cheap (24 ms each) and dilutes the host-side stalls a shared box throws in now and then
     h2d = d2h = 0
 
     import copy
@@ -271,15 +275,21 @@ def main():
         return cnt.segments, b
 
     e2e_step(-1)  # one untimed warm-up: the first call pays for the per-device wave / film / scene-block caches
+    gc.collect()
+    gc.disable()  # as timeit does: a generation-2 collection over torch's object graph is a ~100 ms host stall in one step
     sync()
     te = time.perf_counter()
     e2e_segs = 0
+    e2e_ms = []
     for i in range(e2e_steps):
+        ts = time.perf_counter()
         segs_i, h2d = e2e_step(i)
+        e2e_ms.append((time.perf_counter() - ts) * 1e3)
         d2h = wh * 16
         e2e_segs += segs_i
     sync()
     e2e_t = time.perf_counter() - te
+    gc.enable()
     if dist is not None:
         t = torch.tensor([e2e_t], device=f"cuda:{local_rank}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,7 +364,8 @@ def main():
         "samples_per_sec": world_size * wh * spp / step_s,
         "rays_per_sec_reference_def": world_size * ref_rays / step_s,
         "true_rays_per_sec": world_size * c.true_rays / step_s,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                "rank0_step_ms": {"min": min(e2e_ms), "median": sorted(e2e_ms)[len(e2e_ms) // 2], "max": max(e2e_ms)}},
         "gpu_launches": launches_all,
         "clocks": clocks,
         "roofline": roofline,
