@@ -139,6 +139,34 @@ def test_spp_split_equals_whole(scenes):
     assert np.allclose(a + b, whole, rtol=1e-4, atol=1e-7)
 
 
+def test_full_size_headline_config(pkg):
+    """BASELINE configs[0] at its full size (Cornell 1920x1080 @ 16 spp, the bench workload: one wave of 33.2 M paths, queues
+    of tens of millions of entries, every warp claiming tiles dynamically): primary hit ids over all 2 M pixels, the
+    same-stream film and the Profile counters against the oracle (~15 s of CPU), and the spp-split linearity property."""
+    world, st, flat = parity.load_scene("cornell")
+    assert (st.width, st.height, st.min_samples) == (1920, 1080, 16)
+    cs, os_ = parity.cuda_scene(flat), parity.oracle_scene(flat)
+    p = st.params(seed=77)
+    gi, gp, gt = cs.trace_primary(p)
+    oi, op, ot = os_.trace_primary(p)
+    assert float(np.mean((gi == oi) & (gp == op))) >= 0.9999
+    fg, cg = cs.render_pt(p)
+    fo, co = os_.render_pt(p)
+    assert np.isfinite(fg).all()
+    assert parity.rel_mse(fg, fo) < 1e-6, parity.rel_mse(fg, fo)
+    assert abs(float(fg[..., 1].mean()) - float(fo[..., 1].mean())) / float(fo[..., 1].mean()) < 1e-5
+    assert cg.camera_rays == co.camera_rays == 1920 * 1080 * 16
+    for k in ("bounce_rays", "shadow_rays", "env_hits", "segments"):
+        a, b = getattr(cg, k), getattr(co, k)
+        assert abs(a - b) <= 1e-5 * b, (k, a, b)
+    # linearity: 16 spp == 6 spp + 10 spp with continued sample indices (what the multi-GPU split relies on)
+    a, _ = cs.render_pt(st.params(seed=77, spp=6, spp_offset=0, spp_total=16))
+    b, _ = cs.render_pt(st.params(seed=77, spp=10, spp_offset=6, spp_total=16))
+    assert np.allclose(a + b, fg, rtol=1e-4, atol=1e-7)
+    cs.close()
+    os_.close()
+
+
 def test_empty_and_edge_cases(scenes, pkg):
     st, cs, _ = scenes("cornell", 96, 54, 8)
     film, cnt = cs.render_pt(st.params(seed=1, spp=0))
