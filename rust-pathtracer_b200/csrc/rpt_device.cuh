@@ -90,6 +90,7 @@ struct DevScene {
   const uint32_t *lights;
   // Every instance whose hits carry a Light material, when all of them are analytic shapes (and there are few):
   // lets the NEE visibility query run as "closest light, then any occluder in front of it" (k_shadow).
+  uint32_t min_grab;        // smallest number of queue tiles a warp claims at once (TileStream)
   uint32_t num_light_geom;  // 0 = two-phase NEE visibility disabled
   const uint32_t *light_geom;
   const float *light_geom_box;  // 6 floats (world min, max) per entry: the box the reference's BVH gates the shape with

@@ -228,17 +228,19 @@ __device__ __forceinline__ void flush_count(uint32_t v, uint32_t *dst) {
 // * grab is sized so that a warp makes about CLAIMS_PER_WARP claims per launch whatever the queue length: the balance
 //   granularity stays a few percent of a warp's share, and the claim counter sees a bounded number of atomics (same-address
 //   atomics sustain ~0.7 G/s; a fixed grab of 2 tiles cost a streaming scene - one sphere, a ray is one node test - 33 ms
-//   of a 27 ms kernel).
+//   of a 27 ms kernel). Scenes whose rays are nearly free (a handful of analytic shapes, no mesh) take at least 4 tiles per
+//   claim (DevScene::min_grab): there a claim's latency is long against a tile's work (rtiow2 3.2 -> 2.5 ms per frame), while
+//   for real geometry the finer balance wins (Cornell 21.8 vs 22.3 ms, kitchen_sink 7.5 vs 8.7 ms).
 // * the NEXT claim is issued as soon as the current one is taken up, so its latency overlaps the tiles being processed.
 #define CLAIMS_PER_WARP 32u
 struct TileStream {
   uint32_t *ctr;
   uint32_t n_tiles, grab, cur, lim, pending;
   __device__ __forceinline__ uint32_t claim() const { return (threadIdx.x & 31u) == 0 ? atomicAdd(ctr, grab) : 0u; }
-  __device__ __forceinline__ void init(uint32_t *counter, uint32_t n_tiles_, uint32_t total_warps) {
+  __device__ __forceinline__ void init(uint32_t *counter, uint32_t n_tiles_, uint32_t total_warps, uint32_t min_grab) {
     ctr = counter;
     n_tiles = n_tiles_;
-    grab = min(64u, max(1u, n_tiles_ / (total_warps * CLAIMS_PER_WARP)));
+    grab = min(64u, max(min_grab, n_tiles_ / (total_warps * CLAIMS_PER_WARP)));
     cur = lim = 0;
     pending = claim();
   }
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
     for (uint32_t tile = tile0; tile < n_tiles; tile += total_warps) body(tile);
   } else {
     TileStream ts;
-    ts.init(counts + F_TRACE, n_tiles, total_warps);
+    ts.init(counts + F_TRACE, n_tiles, total_warps, S.min_grab);
     for (uint32_t tile = ts.next(); tile != RPT_NONE; tile = ts.next()) body(tile);
   }
   if (wc_miss.used < QCHUNK) chunk_pad(wc_miss, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
   const uint32_t n_tiles = n_round >> 5;
 #if SHADE_DYNAMIC
   TileStream ts;
-  ts.init(counts + (CLASS == Q_DIFFUSE ? F_SHADE_DIFFUSE : F_SHADE_GGX), n_tiles, gridDim.x * (SHADE_THREADS / 32));
+  ts.init(counts + (CLASS == Q_DIFFUSE ? F_SHADE_DIFFUSE : F_SHADE_GGX), n_tiles, gridDim.x * (SHADE_THREADS / 32), S.min_grab);
   auto next_tile = [&]() -> uint32_t { return ts.next(); };
 #else
   uint32_t g_cur = blockIdx.x * (SHADE_THREADS / 32) + (tid >> 5);
@@ -867,7 +869,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) body(i);
   } else {
     TileStream ts;
-    ts.init(counts + F_SHADOW, n_tiles, gridDim.x * (TRACE_THREADS / 32));
+    ts.init(counts + F_SHADOW, n_tiles, gridDim.x * (TRACE_THREADS / 32), S.min_grab);
     for (uint32_t tile = ts.next(); tile != RPT_NONE; tile = ts.next()) body(tile * 32u + lane);
   }
   flush_work(tw, work);
@@ -1815,6 +1817,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     if (d->instances[i].kind == RPT_AGG_MESH && !flattened[i]) needed_blas_depth = std::max(needed_blas_depth, minfo[d->instances[i].mesh].depth);
   // one push per inner node on the path; shared-memory stack sized to the scene (16 / 32 / 64 / 128 entries per thread)
   uint32_t need = tlas.max_depth + needed_blas_depth + 2;
+  S->dev.min_grab = (leaf_box.size() <= 8 && needed_blas_depth == 0) ? 4u : 1u;
   S->stack_entries = need <= 16 ? 16 : (need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 0)));
   if (S->stack_entries == 0) return bail(fail("BVH deeper than the largest traversal stack (128 entries)"));
   S->stack_smem = (size_t)S->stack_entries * TRACE_THREADS * sizeof(int);
