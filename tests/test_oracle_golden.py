@@ -201,6 +201,30 @@ def test_oracle_cornell_golden_film(pkg):
     sc.close()
 
 
+def test_oracle_golden_films_all_scenes(pkg):
+    """One tiny oracle film per scene blob plus a small importance-map bake, pinned by tests/golden/oracle_films_16x12.npz
+    (tools/make_golden.py): any change to the checker's arithmetic on any material / light / environment / camera path shows
+    up here, on the CPU, before it can silently move the target the GPU is compared with."""
+    import parity
+
+    gold = np.load(os.path.join(GOLDEN, "oracle_films_16x12.npz"))
+    for name in gold.files:
+        if name.startswith("hdri_imap"):
+            continue
+        world, st, flat = parity.load_scene(name, 16, 12, 4)
+        sc = parity.oracle_scene(flat)
+        film, _ = sc.render_pt(st.params(seed=11))
+        sc.close()
+        assert np.allclose(film, gold[name], rtol=1e-4, atol=1e-7), name
+    world, st, flat = parity.load_scene("hdri", 16, 12, 1)
+    sc = parity.oracle_scene(flat)
+    lum, basis = pkg.importance_map.bake_curve_tables(world, pkg.curves.y_bar_curve(), st.wavelength_bounds)
+    bk = sc.bake_importance_map(12, 20, lum, basis, st.wavelength_bounds)
+    sc.close()
+    assert np.allclose(bk["row_cdf"], gold["hdri_imap_row_cdf_12x20"], rtol=1e-6, atol=0)
+    assert np.allclose(bk["marginal_cdf"], gold["hdri_imap_marginal_cdf_12"], rtol=1e-6, atol=0)
+
+
 def test_oracle_furnace_energy(pkg):
     """Exact furnace (SURVEY A9 ii) on the oracle: background pixels see E = 1 directly, so their Y is the
     mean of y_bar over the wavelength range; sphere pixels return the same within Monte-Carlo noise times the

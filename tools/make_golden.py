@@ -38,4 +38,21 @@ world, st, flat = parity.load_scene("cornell", 16, 9, 4)
 sc = parity.oracle_scene(flat)
 film, _ = sc.render_pt(st.params(seed=11))
 np.save(os.path.join(G, "cornell_oracle_16x9.npy"), film)
+# one tiny film per scene blob: pins every oracle code path (materials, lights, environments, instancing, cameras)
+films = {}
+for name in ["cornell", "furnace", "furnace_exact", "gem", "hdri", "test_nee_sphere", "orb_caustic", "sun_test", "rtiow2", "instanced_monkeys", "kitchen_sink"]:
+    world, st, flat = parity.load_scene(name, 16, 12, 4)
+    sc = parity.oracle_scene(flat)
+    films[name], _ = sc.render_pt(st.params(seed=11))
+    sc.close()
+# the importance-map bake (N3) at a small resolution
+world, st, flat = parity.load_scene("hdri", 16, 12, 1)
+sc = parity.oracle_scene(flat)
+p_ = parity.pkg()
+lum, basis = p_.importance_map.bake_curve_tables(world, p_.curves.y_bar_curve(), st.wavelength_bounds)
+bk = sc.bake_importance_map(12, 20, lum, basis, st.wavelength_bounds)
+films["hdri_imap_row_cdf_12x20"] = bk["row_cdf"]
+films["hdri_imap_marginal_cdf_12"] = bk["marginal_cdf"]
+sc.close()
+np.savez_compressed(os.path.join(G, "oracle_films_16x12.npz"), **films)
 print("golden fixtures written to", G)
