@@ -139,6 +139,28 @@ def test_spp_split_equals_whole(scenes):
     assert np.allclose(a + b, whole, rtol=1e-4, atol=1e-7)
 
 
+def test_against_committed_golden_films(pkg):
+    """The CUDA path against the COMMITTED oracle fixtures (tests/golden/oracle_films_16x12.npz, tools/make_golden.py): the
+    same comparison as test_same_stream_images, but with a target that cannot move with the oracle library of the day."""
+    import os
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_films_16x12.npz"))
+    for name in gold.files:
+        if name.startswith("hdri_imap"):
+            continue
+        world, st, flat = parity.load_scene(name, 16, 12, 4)
+        cs = parity.cuda_scene(flat)
+        film, _ = cs.render_pt(st.params(seed=11))
+        cs.close()
+        assert parity.rel_mse(film, gold[name]) < 2e-3 and parity.mean_rel_diff(film, gold[name]) < 2e-3, (name, parity.rel_mse(film, gold[name]))
+    world, st, flat = parity.load_scene("hdri", 16, 12, 1)
+    cs = parity.cuda_scene(flat)
+    lum, basis = pkg.importance_map.bake_curve_tables(world, pkg.curves.y_bar_curve(), st.wavelength_bounds)
+    bk = cs.bake_importance_map(12, 20, lum, basis, st.wavelength_bounds)
+    cs.close()
+    assert np.array_equal(bk["row_cdf"], gold["hdri_imap_row_cdf_12x20"]) and np.array_equal(bk["marginal_cdf"], gold["hdri_imap_marginal_cdf_12"])
+
+
 def test_full_size_headline_config(pkg):
     """BASELINE configs[0] at its full size (Cornell 1920x1080 @ 16 spp, the bench workload: one wave of 33.2 M paths, queues
     of tens of millions of entries, every warp claiming tiles dynamically): primary hit ids over all 2 M pixels, the
