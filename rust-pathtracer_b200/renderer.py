@@ -155,15 +155,17 @@ class CudaRenderer:
 
     def output_film(self, scene: ffi.Scene, rs: RenderSettings, film: Optional[np.ndarray], output_dir: Optional[str] = None, factor: float = 1.0):
         """output_film (reference src/renderer/mod.rs:24-80) with the tonemapping / colour conversion / byte encoding on the
-        device. film=None tonemaps the device-resident film of the scene's last render. File encoding stays on the host:
-        PNG through Pillow when present; the EXR payload (linear RGB) is saved as .npy (no EXR encoder in this image)."""
+        device. film=None tonemaps the device-resident film of the scene's last render. File encoding stays on the host, as
+        in the reference: `<filename>.exr` (linear RGB, f32; exr.py) and `<filename>.png` (Pillow; raw .npy bytes without it)."""
         rgb, rgba, lw = scene.output_film(output_settings(rs, factor), film, rs.width, rs.height)
         if output_dir is not None:
             import os
 
             os.makedirs(output_dir, exist_ok=True)
             name = rs.filename or "beauty"
-            np.save(os.path.join(output_dir, name + ".linear_rgb.npy"), rgb)
+            from .exr import write_exr_rgb
+
+            write_exr_rgb(os.path.join(output_dir, name + ".exr"), rgb)
             try:
                 from PIL import Image
 

@@ -241,6 +241,34 @@ def test_empty_and_edge_cases(scenes, pkg):
         o2.close()
 
 
+def test_public_api_render_writes_exr_and_png(pkg, tmp_path):
+    """Renderer::render end to end: film -> output_film on the device -> `<filename>.exr` (linear RGB) and `<filename>.png`
+    on the host, as renderer/mod.rs:24-80 does. The EXR holds exactly rpt_output_film's linear payload."""
+    import os
+
+    world, st, flat = parity.load_scene("cornell", 48, 27, 4)
+    rs = pkg.loader.RenderSettings(filename="beauty", width=48, height=27, integrator_type="PT", light_samples=st.light_samples,
+                                   medium_aware=False, min_bounces=st.min_bounces, max_bounces=st.max_bounces, hwss=False, threads=1,
+                                   min_samples=4, camera_id="main", russian_roulette=True, only_direct=False, wavelength_bounds=None,
+                                   premultiply=None)
+    rs.raw = {"tonemap_settings": {"type": "Reinhard1", "luminance_only": False, "key_value": 0.18, "white_point": 1.0},
+              "colorspace_settings": {"type": "sRGB"}}
+    cfg = pkg.loader.Config(scene_file="", renderer={"type": "Cuda"}, render_settings=[rs], camera_names_to_index={"main": 0})
+    r = pkg.CudaRenderer(device=0, seed=2)
+    films = r.render(world, cfg, output_dir=str(tmp_path))
+    exr_path, png_path = os.path.join(tmp_path, "beauty.exr"), os.path.join(tmp_path, "beauty.png")
+    assert os.path.exists(exr_path)
+    rgb = pkg.exr.read_exr_rgb(exr_path)
+    sc = r.make_scene(world, st.wavelength_bounds)
+    want, rgba, _ = sc.output_film(pkg.renderer.output_settings(rs), films["beauty"], 48, 27)
+    sc.close()
+    assert np.array_equal(rgb, want)
+    if os.path.exists(png_path):
+        from PIL import Image
+
+        assert np.array_equal(np.asarray(Image.open(png_path)), rgba)
+
+
 def test_public_api_render(pkg):
     """The reference-facing call: CudaRenderer.render(world, config) -> one mean-XYZ film per render setting
     (mirror of `trait Renderer::render`, src/renderer/mod.rs:107-112), checked against the oracle."""

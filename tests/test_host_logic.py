@@ -229,6 +229,29 @@ def test_loader_parses_panorama_camera(pkg):
     assert np.allclose(w.cameras[0].angle_span, (2 * np.pi, np.deg2rad(160.0)), rtol=1e-6)
 
 
+def test_exr_writer_roundtrip(pkg, tmp_path):
+    """output_film's EXR payload (tonemap/mod.rs:225-247): the writer's file is read back by the package's own reader and,
+    when OpenCV was built with OpenEXR, by an independent decoder."""
+    import os
+
+    rng = np.random.default_rng(3)
+    img = rng.uniform(0.0, 8.0, size=(9, 17, 3)).astype(np.float32)
+    img[0, 0] = (0.0, 1e-8, 6.5e4)
+    path = str(tmp_path / "beauty.exr")
+    pkg.exr.write_exr_rgb(path, img)
+    assert open(path, "rb").read(4) == bytes([0x76, 0x2F, 0x31, 0x01])
+    assert np.array_equal(pkg.exr.read_exr_rgb(path), img)
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    try:
+        import cv2
+
+        im = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    except Exception:
+        im = None
+    if im is not None:
+        assert im.dtype == np.float32 and np.array_equal(im[:, :, ::-1], img)
+
+
 def test_distributed_spp_split_reduce_gloo(tmp_path):
     """N > 1 path on CPU: two gloo ranks each render their spp share (CPU oracle as the stand-in renderer for the
     host logic), one reduce(sum) to rank 0, normalise: equals the single-rank render of all samples."""
