@@ -99,6 +99,11 @@ def cpu_oracle_run(parity, spp: int, steps: int, warmup: int):
     """Times the CPU oracle on the bounded sample; returns (segments/s, seconds/step, threads, counters)."""
     world, st, flat = parity.load_scene(SCENE, CPU_SAMPLE[0], CPU_SAMPLE[1], spp)
     sc = parity.oracle_scene(flat)
+    try:
+        host_cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        host_cores = os.cpu_count() or 1
+    sc.lib.rpto_set_num_threads(int(host_cores))  # all the host threads, whatever OMP_NUM_THREADS the launcher exported
     threads = int(sc.lib.rpto_num_threads())
     times, segs, cnt = [], 0, None
     for i in range(warmup + steps):

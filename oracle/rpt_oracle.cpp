@@ -1793,6 +1793,14 @@ uint32_t rpto_tlas_nodes(RptScene *S, uint32_t *triples, uint32_t cap) {
   }
   return n;
 }
+// torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm of the benchmark asks for the host's cores explicitly
+void rpto_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int rpto_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
