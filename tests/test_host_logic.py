@@ -220,6 +220,7 @@ def test_panorama_camera(pkg, oracle):
 def test_loader_parses_panorama_camera(pkg):
     """parsing/cameras.rs:85-93,150-160: `type = "PanoramaCamera"` with fov = [h, v] in degrees; only cameras a render setting
     names are constructed (:131-133)."""
+    import tools_helpers  # noqa: F401  (puts tools/ on sys.path)
     import bake_scenes
 
     cfg = bake_scenes.make_config("data/scenes/kitchen_sink.toml", 64, 32, 1, 2, 8, 2)
@@ -227,6 +228,40 @@ def test_loader_parses_panorama_camera(pkg):
     w = pkg.loader.construct_world(cfg)
     assert len(w.cameras) == 1 and w.cameras[0].kind == 1 and w.cameras[0].name == "pano"
     assert np.allclose(w.cameras[0].angle_span, (2 * np.pi, np.deg2rad(160.0)), rtol=1e-6)
+
+
+@needs_ref
+def test_every_shipped_scene_loads_flattens_and_renders(pkg):
+    """Drop-in check of the host mirror: every data/scenes/*.toml of the reference goes through the loader, the flattening
+    to RptSceneDesc and one tiny oracle render (finite film). The only accepted failure is an asset the reference itself does
+    not ship (missing .obj / texture files)."""
+    import glob
+    import tomllib
+
+    import tools_helpers  # noqa: F401  (puts tools/ on sys.path)
+    import bake_scenes
+    import parity
+
+    loaded, missing = 0, []
+    for f in sorted(glob.glob("/root/reference/data/scenes/*.toml")):
+        rel = os.path.relpath(f, "/root/reference")
+        cams = [c.get("name") for c in tomllib.load(open(f, "rb")).get("cameras", [])]
+        cfg = bake_scenes.make_config(rel, 8, 8, 1, 1, 3, 1)
+        cfg.render_settings[0].camera_id = cams[0] if cams else "main"
+        try:
+            world = pkg.loader.construct_world(cfg)
+        except pkg.loader.LoadError as e:
+            assert "could not find" in str(e), (rel, e)
+            missing.append(os.path.basename(f))
+            continue
+        flat = pkg.ffi.FlatScene(world, 380.0, 750.0, 64)
+        st = pkg.PTSettings.from_render_settings(cfg.render_settings[0], 0)
+        sc = parity.oracle_scene(flat)
+        film, cnt = sc.render_pt(st.params(seed=1))
+        sc.close()
+        assert np.isfinite(film).all() and cnt.camera_rays == 64, rel
+        loaded += 1
+    assert loaded >= 24 and len(missing) <= 6, (loaded, missing)
 
 
 def test_exr_writer_roundtrip(pkg, tmp_path):
