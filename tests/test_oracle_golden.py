@@ -201,6 +201,30 @@ def test_oracle_cornell_golden_film(pkg):
     sc.close()
 
 
+def test_ggx_sampling_weights_conserve_energy(lib):
+    """The reference's test_integral (ggx.rs) only prints; the property it eyeballs is asserted here: with VNDF sampling the
+    estimator weight f |cos| / pdf of a non-absorbing dielectric never exceeds 1 and averages to 1 minus the single-scatter
+    loss (which grows with roughness and towards grazing incidence); a conductor stays below its Fresnel reflectance."""
+    lib.rpto_ggx_generate_and_evaluate.argtypes = [F, F, F, F, ct.c_int, F, F, ct.c_void_p, ct.c_void_p, ct.POINTER(F), ct.POINTER(F)]
+    rng = np.random.default_rng(1)
+    for metallic, eta, kappa in ((0, 1.5, 0.0), (1, 0.2, 3.5)):
+        means = {}
+        for alpha in (0.05, 0.2, 0.5):
+            for cz in (0.95, 0.6, 0.25):
+                wi, wo, f, p = (F * 3)(float(np.sqrt(1 - cz * cz)), 0.0, cz), (F * 3)(), F(), F()
+                w = []
+                for sx, sy in rng.random((1500, 2)):
+                    lib.rpto_ggx_generate_and_evaluate(alpha, eta, 1.0, kappa, metallic, float(sx), float(sy), wi, wo, ct.byref(f), ct.byref(p))
+                    w.append(f.value * abs(wo[2]) / p.value if p.value > 0 else 0.0)
+                assert max(w) <= 1.0 + 1e-3, (metallic, alpha, cz, max(w))
+                means[(alpha, cz)] = float(np.mean(w))
+        if metallic:
+            assert all(0.6 < m < 0.97 for m in means.values()), means
+        else:
+            assert all(0.85 < m <= 1.0 + 1e-3 for m in means.values()), means
+            assert means[(0.05, 0.95)] > 0.999 and means[(0.5, 0.25)] < means[(0.05, 0.25)]
+
+
 def test_oracle_golden_films_all_scenes(pkg):
     """One tiny oracle film per scene blob plus a small importance-map bake, pinned by tests/golden/oracle_films_16x12.npz
     (tools/make_golden.py): any change to the checker's arithmetic on any material / light / environment / camera path shows
