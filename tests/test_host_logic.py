@@ -264,6 +264,57 @@ def test_every_shipped_scene_loads_flattens_and_renders(pkg):
     assert loaded >= 24 and len(missing) <= 6, (loaded, missing)
 
 
+def test_oracle_closest_hits_against_brute_force(pkg):
+    """The oracle's World::hit (two BVH levels, watertight triangle test, tie rules) against an independent float64
+    brute force over every triangle of the Cornell meshes plus the light rect: same (instance, primitive) for random rays
+    from inside the box, same t to 1e-5. This is what the GPU's hit-id parity ultimately rests on."""
+    import parity
+
+    world, st, flat = parity.load_scene("cornell", 8, 8, 1)
+    sc = parity.oracle_scene(flat)
+    rng = np.random.default_rng(5)
+    n = 4000
+    o = rng.uniform(0.02, 0.53, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o32, d32 = o.astype(np.float32), d.astype(np.float32)
+    oi, op, ot = sc.trace_rays(o32, d32, np.full(n, np.inf, dtype=np.float32))
+    sc.close()
+    o, d = o32.astype(np.float64), d32.astype(np.float64)
+    best_t = np.full(n, np.inf)
+    best_inst = np.full(n, 0xFFFFFFFF, dtype=np.uint64)
+    best_prim = np.full(n, 0xFFFFFFFF, dtype=np.uint64)
+    for ii, inst in enumerate(world.instances):
+        if inst.kind == 3:  # mesh: Moeller-Trumbore, both sides
+            m = world.meshes[inst.mesh]
+            v = np.asarray(m.vertices, dtype=np.float64)
+            for f, (a, b, c) in enumerate(np.asarray(m.indices)):
+                e1, e2 = v[b] - v[a], v[c] - v[a]
+                pv = np.cross(d, e2)
+                det = pv @ e1
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    tv = o - v[a]
+                    u = np.einsum("ij,ij->i", tv, pv) / det
+                    qv = np.cross(tv, e1)
+                    w = np.einsum("ij,ij->i", d, qv) / det
+                    t = (qv @ e2) / det
+                hit = (np.abs(det) > 1e-14) & (u >= 0) & (w >= 0) & (u + w <= 1) & (t > 0) & (t < best_t)
+                best_t[hit], best_inst[hit], best_prim[hit] = t[hit], ii, f
+        else:  # the light: an axis-aligned rect with normal Z (rect.rs:69-111)
+            assert inst.kind == 0 and inst.axis == 2
+            t = (inst.origin[2] - o[:, 2]) / d[:, 2]
+            x, y = o[:, 0] + t * d[:, 0], o[:, 1] + t * d[:, 1]
+            hit = (t > 0) & (np.abs(x - inst.origin[0]) <= inst.size[0] / 2) & (np.abs(y - inst.origin[1]) <= inst.size[1] / 2) & (t < best_t)
+            if not inst.two_sided:
+                pass  # a one-sided rect is still hit from behind (rect.rs:96-100 only flips the normal of two-sided ones)
+            best_t[hit], best_inst[hit], best_prim[hit] = t[hit], ii, 0
+    same = (best_inst == oi) & ((best_prim == op) | (best_inst == 0xFFFFFFFF))
+    print(f"oracle vs brute force: {same.mean():.5f} of {n} rays agree")
+    assert same.mean() >= 0.998, same.mean()  # edge-on / shared-edge rays may legitimately pick the neighbouring triangle
+    both = same & (best_inst != 0xFFFFFFFF)
+    assert np.allclose(ot[both], best_t[both], rtol=1e-5, atol=1e-6)
+
+
 def test_exr_writer_roundtrip(pkg, tmp_path):
     """output_film's EXR payload (tonemap/mod.rs:225-247): the writer's file is read back by the package's own reader and,
     when OpenCV was built with OpenEXR, by an independent decoder."""
