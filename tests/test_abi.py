@@ -32,7 +32,8 @@ def test_library_exports_every_declared_symbol(pkg):
 
 
 def test_oracle_exports_the_same_surface(pkg, oracle):
-    for name in ("scene_create", "scene_destroy", "render_pt", "trace_primary", "trace_rays", "last_error", "abi_version"):
+    for name in ("scene_create", "scene_destroy", "render_pt", "trace_primary", "trace_rays", "last_error", "abi_version", "output_film",
+                 "scene_bake_importance_map", "render_samples", "set_num_threads", "num_threads"):
         assert hasattr(oracle, "rpto_" + name)
     assert oracle.rpto_abi_version() == pkg.ffi.ABI_VERSION
 
