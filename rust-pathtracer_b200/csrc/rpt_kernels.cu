@@ -1234,6 +1234,7 @@ struct RptScene {
   uint32_t stack_entries = 16;
   size_t stack_smem = 0;
   uint32_t env_stack_count = 0;  // textures in the environment's stack (HDR)
+  bool has_ggx = true;     // any material of the GGX class (else its shade kernel is never launched)
   bool tma_tiles = false;  // k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
   // timing of the last render
   std::vector<cudaEvent_t> ev_pool;
@@ -1542,9 +1543,11 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       T.begin(K_SHADE_DIFFUSE);
       k_shade_surface<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
       T.end();
-      T.begin(K_SHADE_GGX);
-      k_shade_surface<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
-      T.end();
+      if (S->has_ggx) {  // (no GGX material in the scene: the class list stays empty, skip its 12 launches per wave)
+        T.begin(K_SHADE_GGX);
+        k_shade_surface<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
+        T.end();
+      }
       if (P->light_samples > 0) {
         T.begin(K_SHADOW);
         k_shadow<<<S->grid[K_SHADOW], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc, w.work + 3);
@@ -1894,6 +1897,8 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   rc |= B.upload(light_geom_box.data(), light_geom_box.size(), &D.light_geom_box);
   D.num_light_geom = (uint32_t)light_geom.size();
   rc |= B.upload(d->materials, d->num_materials, &D.materials);
+  S->has_ggx = false;
+  for (uint32_t i = 0; i < d->num_materials; ++i) S->has_ggx |= d->materials[i].type == RPT_MATERIAL_GGX;
   rc |= B.upload(d->curve_lut, (size_t)d->num_curves * d->num_lambda, &D.curve_lut);
   rc |= B.upload(d->cie_lut, 3 * (size_t)d->num_lambda, &D.cie_lut);
   if (rc) return bail(rc);
