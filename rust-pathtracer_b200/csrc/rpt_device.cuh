@@ -415,9 +415,14 @@ __device__ __forceinline__ bool tri_test(float3 p0, float3 p1, float3 p2, float3
 }
 
 // Robust slab test against one child box; tnear returned for ordering. Conservative (never rejects a
-// box the exact test accepts): the far plane is widened by 2*gamma(3) as in PBRT's Bounds3::IntersectP, and
-// a NaN lane (0 * inf) drops that axis' constraint. This is the one place that uses explicit FMAs
-// (t = b * inv_d - o * inv_d): it only prunes, it never decides a hit, so its rounding is parity-irrelevant.
+// box the exact test accepts): the far plane is widened by 2*gamma(3) as in PBRT's Bounds3::IntersectP. This is
+// the one place that uses explicit FMAs (t = b * inv_d - o * inv_d): it only prunes, it never decides a hit, so
+// its rounding is parity-irrelevant.
+// Zero direction components: the reference leaves such an axis unconstrained (aabb.rs:41-45: d == 0 -> (0, +inf)).
+// b * (+-inf) - o * (+-inf) does NOT do that by itself (it is NaN only when b and o have the same sign, +-inf
+// otherwise, and fmin/fmax then keep the infinite plane and reject the box), so slab_recip() poisons o * inv_d with
+// a NaN on those axes: both plane distances become NaN and fminf / fmaxf drop the axis, at no cost per node.
+__device__ __forceinline__ void slab_recip(float3 o, float3 d, float3 &inv, float3 &oinv);
 __device__ __forceinline__ bool slab_test(float3 bmin, float3 bmax, float3 oinv, float3 inv_d, float tmax, float &tnear) {
   float tx0 = fmaf(bmin.x, inv_d.x, -oinv.x), tx1 = fmaf(bmax.x, inv_d.x, -oinv.x);
   float ty0 = fmaf(bmin.y, inv_d.y, -oinv.y), ty1 = fmaf(bmax.y, inv_d.y, -oinv.y);
@@ -463,6 +468,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+__device__ __forceinline__ void slab_recip(float3 o, float3 d, float3 &inv, float3 &oinv) {
+  const float qnan = __int_as_float(0x7fffffff);
+  inv = f3(rcp_approx(d.x), rcp_approx(d.y), rcp_approx(d.z));
+  oinv = f3(d.x == 0.0f ? qnan : o.x * inv.x, d.y == 0.0f ? qnan : o.y * inv.y, d.z == 0.0f ? qnan : o.z * inv.z);
 }
 
 // Watertight-test constants that depend only on the ray (mesh.rs:76-100 computes them per triangle; hoisting
@@ -536,8 +546,7 @@ struct Trav {
   __device__ __forceinline__ void set_space(float3 no, float3 nd) {
     ro = no;
     rd = nd;
-    inv = f3(rcp_approx(rd.x), rcp_approx(rd.y), rcp_approx(rd.z));
-    oinv = f3(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+    slab_recip(ro, rd, inv, oinv);
     tr = tri_ray_setup(rd);
   }
   __device__ __forceinline__ void init(const DevScene &S, float3 o_, float3 d_, float tmax_) {

@@ -810,8 +810,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
           // disk outside it is unreachable through the reference's BVH; the traversal reproduces that through the leaf
           // box, phase A has to gate on the same box.
           const float *bx = S.light_geom_box + 6 * k;
-          const float3 winv = f3(rcp_approx(d.x), rcp_approx(d.y), rcp_approx(d.z));
-          const float3 woinv = f3(o.x * winv.x, o.y * winv.y, o.z * winv.z);
+          float3 winv, woinv;
+          slab_recip(o, d, winv, woinv);
           float tn;
           if (!slab_test(f3(__ldg(bx), __ldg(bx + 1), __ldg(bx + 2)), f3(__ldg(bx + 3), __ldg(bx + 4), __ldg(bx + 5)), woinv, winv, tl, tn)) continue;
         }

@@ -64,6 +64,44 @@ def test_random_rays(scenes, name):
     assert frac >= 0.9999, f"{name}: {frac:.6f}"
 
 
+def axis_aligned_rays(rng, n, lo, hi):
+    """Rays with one or two exactly-zero direction components (+0 and -0), origins off the planes x/y/z = 0
+    (b * inf - o * inf is NaN or +-inf depending on signs; the slab test must leave such an axis unconstrained
+    like aabb.rs:41-45 does)."""
+    o = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    kind = rng.integers(0, 3, size=n)          # 0: one zero component, 1: two zero components, 2: all nonzero (control)
+    ax = rng.integers(0, 3, size=n)
+    neg = rng.integers(0, 2, size=n).astype(bool)
+    zero = np.where(neg, np.float32(-0.0), np.float32(0.0))
+    for i in range(n):
+        if kind[i] == 0:
+            d[i, ax[i]] = zero[i]
+        elif kind[i] == 1:
+            d[i, (ax[i] + 1) % 3] = zero[i]
+            d[i, (ax[i] + 2) % 3] = -zero[i]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o, d.astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["cornell", "gem", "test_nee_sphere", "instanced_monkeys", "kitchen_sink", "rtiow2"])
+def test_axis_aligned_rays(scenes, name):
+    """Rays with exactly-zero direction components hit what the oracle hits (bit-exact ids); a third of the batch is
+    a control group of general rays through the same code path."""
+    st, cs, os_ = scenes(name, 64, 64, 1)
+    rng = np.random.default_rng(17)
+    n = 12000
+    scale = {"instanced_monkeys": 40.0, "kitchen_sink": 3.0}.get(name, 1.0)
+    lo, hi = (-0.9 * scale, 0.9 * scale) if name != "cornell" else (0.01, 0.54)
+    o, d = axis_aligned_rays(rng, n, lo, hi)
+    tmax = np.full(n, np.inf, dtype=np.float32)
+    gi, gp, gt = cs.trace_rays(o, d, tmax)
+    oi, op, ot = os_.trace_rays(o, d, tmax)
+    same = (gi == oi) & (gp == op)
+    assert (oi != 0xFFFFFFFF).mean() > 0.2, "the batch should hit something"
+    assert same.mean() >= 0.9999, f"{name}: {same.mean():.6f}; first mismatches {np.flatnonzero(~same)[:5]}"
+
+
 @pytest.mark.parametrize("name", ALL_SCENES + ["instanced_monkeys"])
 def test_same_stream_images(scenes, name):
     """Same Philox streams on both sides: the low-spp images agree far below the noise floor.

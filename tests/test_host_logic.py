@@ -276,6 +276,12 @@ def test_oracle_closest_hits_against_brute_force(pkg):
     n = 4000
     o = rng.uniform(0.02, 0.53, size=(n, 3))
     d = rng.normal(size=(n, 3))
+    # a quarter of the rays are axis-aligned in one or two components (exact +-0): the reference leaves such an axis of the
+    # slab test unconstrained (aabb.rs:41-45), which is what the device's slab_recip() has to reproduce
+    for i in range(0, n, 4):
+        d[i, i % 3] = 0.0 if (i // 4) % 2 else -0.0
+        if (i // 12) % 2:
+            d[i, (i + 1) % 3] = 0.0
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     o32, d32 = o.astype(np.float32), d.astype(np.float32)
     oi, op, ot = sc.trace_rays(o32, d32, np.full(n, np.inf, dtype=np.float32))
