@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RPT_ABI_VERSION 7u
+#define RPT_ABI_VERSION 8u
 
 /* ---- MaterialId (reference src/materials/mod.rs:22-27) --------------------------
  * Packed as (tag << 16) | table_index; RPT_MAT_NONE = "no override / no id". */
@@ -197,7 +197,13 @@ typedef struct RptRenderParams {
   float lambda_lo, lambda_hi; /* wavelength_bounds */
   uint32_t camera;            /* index into cameras[] */
   uint64_t seed;              /* Philox key */
+  uint32_t flags;             /* RPT_FLAG_*: run-time instrumentation, off by default */
+  uint32_t reserved;          /* 0 */
 } RptRenderParams;
+
+/* RptRenderParams.flags. Instrumentation is opt-in: a plain render records two CUDA events and carries no counters. */
+#define RPT_FLAG_KERNEL_TIMES 1u /* CUDA events around every kernel launch -> rpt_last_kernel_times() */
+#define RPT_FLAG_BVH_STATS 2u    /* nodes / triangles / instances visited -> RptCounters.walk_* / shadow_* (else 0) */
 
 /* Profile counters (reference src/profile.rs:1-8) + true BVH-query counts. */
 typedef struct RptCounters {
@@ -312,6 +318,13 @@ typedef struct RptImapBake {
  * — exactly the payload of the reference's on-disk cache (:254-324), whose bincode encoding stays on the host. */
 int rpt_scene_bake_importance_map(RptScene *scene, const RptImapBake *bake, float *row_pdf, float *row_cdf, float *marginal_pdf,
                                   float *marginal_cdf, float *marginal_integral);
+
+/* Bandwidth probe: the measured denominators of the roofline fractions (north_star: "achieved HBM/L2 GB/s ... against B200
+ * peak"; SURVEY §8d asks for an L2-resident streaming-kernel peak measured on the box). Allocates `bytes`, runs the pattern
+ * `reps` times per launch, returns the best of 4 timed launches in GB/s. mode 0: streaming 128-bit reads (L2 bandwidth when
+ * bytes fits L2, HBM read bandwidth when far larger); mode 1: copy (read + write); mode 2: random 64-byte gathers (the BVH
+ * node fetch pattern). Measurement infrastructure; not used by any render call. */
+int rpt_probe_bandwidth(int device, uint64_t bytes, uint32_t reps, int mode, double *gbps);
 
 /* BVH statistics for roofline accounting: bytes of nodes / primitives. */
 typedef struct RptSceneStats {

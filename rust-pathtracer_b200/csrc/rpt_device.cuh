@@ -23,12 +23,13 @@
 #define RPT_NORMAL_OFFSET 0.001f /* reference src/lib.rs:48 */
 #define RPT_NONE 0xFFFFFFFFu
 #define RPT_INF __int_as_float(0x7f800000)
-// BVH work counters (nodes / triangles / instances visited, reported through RptCounters): compiled in unless RPT_NO_TRAV_STATS
-#ifdef RPT_NO_TRAV_STATS
-#define RPT_STAT(x) ((void)0)
-#else
-#define RPT_STAT(x) x
-#endif
+// BVH work counters (nodes / triangles / instances visited, reported through RptCounters) are a RUN-TIME opt-in
+// (RptRenderParams.flags & RPT_FLAG_BVH_STATS): the traversal code is instantiated with and without them (template
+// parameter STATS), so a plain render carries no instrumentation.
+#define RPT_STAT(x)  \
+  do {               \
+    if (STATS) { x; } \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // Device scene (SoA buffers in HBM; pointers passed by value inside DevScene as a kernel param)
@@ -113,6 +114,13 @@ struct DevScene {
   uint32_t imap_rows, imap_cols, imap_marginal_n;
   const float *imap_row_pdf, *imap_row_cdf, *imap_m_pdf, *imap_m_cdf;
   float imap_marginal_integral;
+  // Small-scene mode (<= RPT_SMALL_MAX leaves, no BLAS): the traversal kernels skip the BVH and test every leaf for every
+  // ray in a warp-uniform loop out of shared memory (32 of 32 lanes busy, no stack); see SmallTrav below.
+  uint32_t small_n;          // 0 = mode off; else the number of leaves
+  uint32_t small_ntri;       // leaves [0, small_ntri) are triangles, [small_ntri, small_n) whole analytic instances
+  const float4 *small_tris;  // per triangle leaf 9 float4: the three vertices in each of the 3 watertight axis permutations
+  const uint4 *small_leaves; // per leaf: instance id, mesh-local triangle id, triangle candidate order, instance candidate order
+  const float *small_boxes;  // per instance leaf (index k - small_ntri) 6 floats: the box the reference's BVH gates the shape with
   float3 world_center; // centre of the scene bounds (ray binning only)
   float p_env;         // effective env sampling probability (1 when there are no lights)
   float world_radius;  // World.radius (world/mod.rs:69-72); informational
@@ -591,14 +599,14 @@ struct Trav {
   // "while-while": the inner loop keeps every lane of the warp on the node-test code until each has reached a
   // leaf (or run out of work); leaves are then processed together, so the warp reconverges at the end of the
   // inner loop instead of drifting apart iteration by iteration.
-  template <bool ANY_HIT>
+  template <bool ANY_HIT, bool STATS>
   __device__ __forceinline__ void run(const DevScene &S, int *stack, int stride, TraceWork &work) {
-    while (!step<ANY_HIT>(S, stack, stride, work)) {
+    while (!step<ANY_HIT, STATS>(S, stack, stride, work)) {
     }
   }
   // One iteration of the outer loop: descend to the next leaf, process it, fetch the next node ref.
   // Returns true when the ray is finished (nothing left to visit, or ANY_HIT accepted a hit).
-  template <bool ANY_HIT>
+  template <bool ANY_HIT, bool STATS>
   __device__ __forceinline__ bool step(const DevScene &S, int *stack, int stride, TraceWork &work) {
     {
       // ---- phase 1: descend through inner nodes (inner refs are >= 0)
@@ -688,15 +696,132 @@ struct Trav {
   }
 };
 
-template <bool ANY_HIT>
+template <bool ANY_HIT, bool STATS>
 __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d, float tmax, int *stack, int stride, TraceHit &out,
                                           TraceWork &work) {
   Trav t;
   t.init(S, o, d, tmax);
-  t.template run<ANY_HIT>(S, stack, stride, work);
+  t.template run<ANY_HIT, STATS>(S, stack, stride, work);
   out = t.out;
   return t.found;
 }
+
+// MeshTriangleRef::hit on vertices that are ALREADY translated by the ray origin and permuted (tri_shuffle commutes with
+// the subtraction component by component, so the arithmetic below is the arithmetic of tri_test_pre, rounding for rounding).
+__device__ __forceinline__ bool tri_test_shuffled(float3 p0t, float3 p1t, float3 p2t, const TriRay &tr, float t0, float t1, float &t_out) {
+  p0t.x = __fadd_rn(p0t.x, __fmul_rn(tr.sx, p0t.z));
+  p1t.x = __fadd_rn(p1t.x, __fmul_rn(tr.sx, p1t.z));
+  p2t.x = __fadd_rn(p2t.x, __fmul_rn(tr.sx, p2t.z));
+  p0t.y = __fadd_rn(p0t.y, __fmul_rn(tr.sy, p0t.z));
+  p1t.y = __fadd_rn(p1t.y, __fmul_rn(tr.sy, p1t.z));
+  p2t.y = __fadd_rn(p2t.y, __fmul_rn(tr.sy, p2t.z));
+  float e0 = __fsub_rn(__fmul_rn(p1t.x, p2t.y), __fmul_rn(p1t.y, p2t.x));
+  float e1 = __fsub_rn(__fmul_rn(p2t.x, p0t.y), __fmul_rn(p2t.y, p0t.x));
+  float e2 = __fsub_rn(__fmul_rn(p0t.x, p1t.y), __fmul_rn(p0t.y, p1t.x));
+  if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+    e0 = (float)__dsub_rn(__dmul_rn((double)p2t.y, (double)p1t.x), __dmul_rn((double)p2t.x, (double)p1t.y));
+    e1 = (float)__dsub_rn(__dmul_rn((double)p0t.y, (double)p2t.x), __dmul_rn((double)p0t.x, (double)p2t.y));
+    e2 = (float)__dsub_rn(__dmul_rn((double)p1t.y, (double)p0t.x), __dmul_rn((double)p1t.x, (double)p0t.y));
+  }
+  if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+  float det = __fadd_rn(__fadd_rn(e0, e1), e2);
+  if (det == 0.0f) return false;
+  float z0 = __fmul_rn(p0t.z, tr.sz), z1 = __fmul_rn(p1t.z, tr.sz), z2 = __fmul_rn(p2t.z, tr.sz);
+  float t_scaled = __fadd_rn(__fadd_rn(__fmul_rn(e0, z0), __fmul_rn(e1, z1)), __fmul_rn(e2, z2));
+  float lo = __fmul_rn(t0, det), hi = __fmul_rn(t1, det);
+  if ((det < 0.0f && (t_scaled >= lo || t_scaled < hi)) || (det > 0.0f && (t_scaled <= lo || t_scaled > hi))) return false;
+  t_out = __fmul_rn(t_scaled, 1.0f / det);
+  return true;
+}
+
+// Small-scene closest / any hit: no BVH. Scenes of a few dozen primitives (the Cornell box: 30 triangles and a rect)
+// fit shared memory whole, and a BVH walk over them runs 11-15 of 32 lanes (ncu, profiles/r01_final_ncu_kernels.csv)
+// because every lane is at a different node. Here the warp walks the leaf list in lockstep - leaf k is the same
+// primitive for all 32 lanes, fetched as a shared-memory broadcast - so no lane idles, there is no stack, and the
+// result is the same by construction: the accept rule (closest t, then the reference's candidate-order tie key) does not
+// depend on the order candidates are visited in. A lane reads its triangle already permuted for its own dominant ray
+// axis (three copies per triangle, 144 B), which removes the per-vertex selects of tri_shuffle from the inner loop.
+// All 32 lanes of the warp must call run() (ANY_HIT votes); `active` masks the lanes that carry a ray.
+#define RPT_SMALL_MAX 64u
+struct SmallTrav {
+  float closest;
+  uint64_t best_key;
+  bool found;
+  TraceHit out;
+  __device__ __forceinline__ void init(float tmax) {
+    closest = tmax;
+    best_key = 0;
+    found = false;
+    out.t = RPT_INF;
+    out.inst = RPT_NONE;
+    out.prim = RPT_NONE;
+  }
+  __device__ __forceinline__ bool accept(float t, uint64_t key, uint32_t inst, uint32_t prim) {
+    if (!found || t < closest || key > best_key) {
+      closest = t;
+      best_key = key;
+      found = true;
+      out.t = t;
+      out.inst = inst;
+      out.prim = prim;
+      return true;
+    }
+    return false;
+  }
+  // s_tris: the CTA's shared-memory copy of DevScene::small_tris. Returns with `found` / `out` / `closest` / `best_key` set.
+  template <bool ANY_HIT, bool STATS>
+  __device__ __forceinline__ void run(const DevScene &S, const float4 *s_tris, float3 o, float3 d, float tmax, bool active, TraceWork &work) {
+    const TriRay tr = tri_ray_setup(d);
+    const float3 os = tri_shuffle(o, tr.kz);
+    bool alive = active;
+    const uint32_t ntri = S.small_ntri, n = S.small_n;
+    for (uint32_t k = 0; k < ntri; ++k) {
+      if (ANY_HIT && !__any_sync(0xFFFFFFFFu, alive)) return;
+      if (alive) {
+        RPT_STAT(work.tris++);
+        const float4 *tv = s_tris + 9u * k + 3u * tr.kz;
+        float4 a = tv[0], b = tv[1], c = tv[2];
+        float t;
+        if (tri_test_shuffled(f3(a) - os, f3(b) - os, f3(c) - os, tr, 0.0f, closest, t)) {
+          uint4 lf = __ldg(S.small_leaves + k);
+          if (accept(t, tie_key(false, lf.w, lf.z), lf.x, lf.y) && ANY_HIT) alive = false;
+        }
+      }
+    }
+    for (uint32_t k = ntri; k < n; ++k) {
+      if (ANY_HIT && !__any_sync(0xFFFFFFFFu, alive)) return;
+      if (alive) {
+        RPT_STAT(work.insts++);
+        uint4 lf = __ldg(S.small_leaves + k);
+        const DevInstance &I = S.instances[lf.x];
+        uint32_t flags = I.flags;
+        float3 lo = o, ld = d;
+        if (flags & DI_HAS_TRANSFORM) {  // instance.rs:89-95
+          lo = xform_point(I.rev, o);
+          ld = xform_vec(I.rev, d);
+        }
+        uint32_t kind = flags & DI_KIND_MASK;
+        float t;
+        bool hit;
+        if (kind == RPT_AGG_RECT) {
+          hit = rect_test(I, lo, ld, 0.0f, closest, tmax, t);
+        } else if (kind == RPT_AGG_SPHERE) {
+          hit = sphere_test(I, lo, ld, 0.0f, closest, tmax, t);
+        } else {
+          // A disk's bounding box is SMALLER than the disk (disk.rs:23-28: half extent radius / 2): the part outside it
+          // is unreachable through the reference's BVH, so the disk is gated on that box here as a BVH leaf would be.
+          const float *bx = S.small_boxes + 6u * (k - ntri);
+          float3 winv, woinv;
+          slab_recip(o, d, winv, woinv);
+          float tn;
+          hit = slab_test(f3(__ldg(bx), __ldg(bx + 1), __ldg(bx + 2)), f3(__ldg(bx + 3), __ldg(bx + 4), __ldg(bx + 5)), woinv, winv, closest, tn) &&
+                disk_test(I, lo, ld, 0.0f, closest, tmax, t);
+        }
+        if (hit && accept(t, tie_key(kind == RPT_AGG_SPHERE, lf.w, 0), lf.x, 0) && ANY_HIT) alive = false;
+      }
+    }
+  }
+};
 
 // Full hit record of a known (instance, primitive, t): Instance::hit's output (instance.rs:96-116).
 struct SurfaceHit {

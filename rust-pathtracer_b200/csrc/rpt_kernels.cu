@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,7 @@ extern "C" int rpt_debug_set_slot(uint32_t slot) { return cudaMemcpyToSymbol(d_d
 namespace {
 
 thread_local std::string g_error;
+std::mutex g_cache_mu;  // guards the process-global per-device caches (DeviceBuffers::spare, g_wave_cache) and cudaFuncSetAttribute
 int fail(const std::string &msg) {
   g_error = msg;
   return 1;
@@ -72,7 +74,6 @@ enum : uint32_t {
   F_TRACE = 12, F_SHADOW = 13, F_SHADE_DIFFUSE = 14, F_SHADE_GGX = 15,  // claim counters of the dynamic tile hand-out (TileStream)
   Q_COUNT = 16
 };
-#define RPT_MAX_BOUNCES 64
 
 struct RenderCtx {
   uint32_t width, height, wh;
@@ -91,7 +92,7 @@ struct WaveBuffers {
   float4 *sh_a, *sh_b;  // shadow records: (origin.xyz, pre-contribution), (dir.xyz, lambda)
   uint32_t *sh_c;       // slot | kind << 31 (1 = environment any-hit)
   float *acc;           // per-slot energy (pt.rs `sum.energy`)
-  uint32_t *counts;     // [RPT_MAX_BOUNCES + 1][Q_COUNT]
+  uint32_t *counts;     // [bounces + 1][Q_COUNT] (RptScene::counts_cap rows)
   unsigned long long *work;  // [2][3]: (nodes, triangles, instances) visited by k_trace / k_shadow
 };
 
@@ -338,14 +339,24 @@ __device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t m
 // Closest-hit traversal of the path queue; appends each path to the list of its vertex's class.
 // RAYGEN: the launch of bounce 0 generates its camera vertices itself (and writes them out for the shade kernel) instead
 // of reading what a separate ray-generation kernel wrote: one 64-byte queue write + read per sample less.
-template <bool TMA, bool RAYGEN = false>
+enum : int { TRAV_BVH = 0, TRAV_BVH_TMA = 1, TRAV_SMALL = 2 };  // how the traversal kernels find hits (chosen per scene)
+
+// Copies the small-scene triangle table into the CTA's dynamic shared memory (TRAV_SMALL only).
+__device__ __forceinline__ void stage_small_tris(const DevScene &S, float4 *s_tris) {
+  for (uint32_t i = threadIdx.x; i < 9u * S.small_ntri; i += blockDim.x) s_tris[i] = __ldg(S.small_tris + i);
+  __syncthreads();
+}
+
+template <int MODE, bool RAYGEN, bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
                                                          uint32_t *__restrict__ q_miss, uint32_t *__restrict__ q_diffuse,
                                                          uint32_t *__restrict__ q_ggx, uint32_t *__restrict__ counts,
                                                          unsigned long long *__restrict__ work, float *__restrict__ acc,
-                                                         RenderCtx R = RenderCtx{}, PathRec *__restrict__ paths_out = nullptr) {
+                                                         RenderCtx R, PathRec *__restrict__ paths_out) {
+  constexpr bool TMA = MODE == TRAV_BVH_TMA;
   static_assert(!(TMA && RAYGEN), "the fused ray generation has no input queue to stage");
-  extern __shared__ int s_stack[];  // [stack entry][thread]; depth chosen per scene at rpt_scene_create
+  extern __shared__ int s_stack[];  // BVH: [stack entry][thread], depth chosen per scene at rpt_scene_create; SMALL: the triangle table
+  if (MODE == TRAV_SMALL) stage_small_tris(S, reinterpret_cast<float4 *>(s_stack));
   // Queue read, two selectable forms (rpt_scene_create picks one; RPT_TMA_TILES=1 selects the TMA form):
   //  * TMA-staged tiles: each warp owns two 2 KB buffers (32 path records each) and two mbarriers. Lane 0 arms the
   //    barrier with the tile's byte count and issues one cp.async.bulk (UBLKCP) for the NEXT tile; the warp traces
@@ -412,10 +423,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
       r.r3 = __ldg(rp + 3);
     }
     if (active) active = __float_as_uint(r.r3.x) != RPT_NONE;  // padding of an abandoned chunk tail
+    TraceHit th;
+    bool hit = false;
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
     if (active) {
-      float3 o = rec_origin(r), d = f3(r.r2);
-      TraceHit th;
-      bool hit = trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+      o = rec_origin(r);
+      d = f3(r.r2);
+    }
+    if (MODE == TRAV_SMALL) {
+      SmallTrav sv;
+      sv.init(RPT_INF);
+      sv.template run<false, STATS>(S, reinterpret_cast<const float4 *>(s_stack), o, d, RPT_INF, active, tw);
+      hit = sv.found;
+      th = sv.out;
+    } else if (active) {
+      hit = trace_ray<false, STATS>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+    }
+    if (active) {
       HitRec h;
       h.t = th.t;
       h.inst = th.inst;
@@ -458,7 +482,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
     n_diffuse += cls == Q_DIFFUSE;
     n_ggx += cls == Q_GGX;
   };
-  if (TMA || !TRACE_DYNAMIC) {
+  if (TMA || (!TRACE_DYNAMIC && MODE != TRAV_SMALL)) {
     for (uint32_t tile = tile0; tile < n_tiles; tile += total_warps) body(tile);
   } else {
     TileStream ts;
@@ -471,7 +495,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
   flush_count(n_miss, counts + N_MISS);
   flush_count(n_diffuse, counts + N_DIFFUSE);
   flush_count(n_ggx, counts + N_GGX);
-  flush_work(tw, work);
+  if (STATS) flush_work(tw, work);
 }
 
 // Environment vertex (integrator/utils.rs:344-373 + pt.rs:487-511).
@@ -770,27 +794,138 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
   flush_count(n_nan, counts + Q_NAN);
 }
 
+// Phase A of the two-phase NEE visibility query: the closest hit among the scene's few analytic light-material shapes
+// (DevScene::light_geom), with the reference's tie rule. Returns false when the ray meets none of them.
+template <bool STATS>
+__device__ __forceinline__ bool shadow_closest_light(const DevScene &S, float3 o, float3 d, float &tl, uint64_t &key_l, uint32_t &inst_l, TraceWork &tw) {
+  bool found_l = false;
+  for (uint32_t k = 0; k < S.num_light_geom; ++k) {
+    uint32_t li = __ldg(S.light_geom + k);
+    const DevInstance &I = S.instances[li];
+    uint32_t flags = I.flags;
+    if ((flags & DI_KIND_MASK) == RPT_AGG_DISK) {
+      // A disk's bounding box is SMALLER than the disk (disk.rs:23-28: half extent radius / 2), so the part of the
+      // disk outside it is unreachable through the reference's BVH; the traversal reproduces that through the leaf
+      // box, phase A has to gate on the same box.
+      const float *bx = S.light_geom_box + 6 * k;
+      float3 winv, woinv;
+      slab_recip(o, d, winv, woinv);
+      float tn;
+      if (!slab_test(f3(__ldg(bx), __ldg(bx + 1), __ldg(bx + 2)), f3(__ldg(bx + 3), __ldg(bx + 4), __ldg(bx + 5)), woinv, winv, tl, tn)) continue;
+    }
+    float3 lo = o, ld = d;
+    if (flags & DI_HAS_TRANSFORM) {
+      lo = xform_point(I.rev, o);
+      ld = xform_vec(I.rev, d);
+    }
+    uint32_t kind = flags & DI_KIND_MASK;
+    float t;
+    bool hit = kind == RPT_AGG_RECT ? rect_test(I, lo, ld, 0.0f, tl, RPT_INF, t)
+                                    : (kind == RPT_AGG_SPHERE ? sphere_test(I, lo, ld, 0.0f, tl, RPT_INF, t) : disk_test(I, lo, ld, 0.0f, tl, RPT_INF, t));
+    RPT_STAT(tw.insts++);
+    if (hit) {
+      uint64_t key = tie_key(kind == RPT_AGG_SPHERE, I.order, 0);
+      if (!found_l || t < tl || key > key_l) {
+        tl = t;
+        key_l = key;
+        found_l = true;
+        inst_l = li;
+      }
+    }
+  }
+  return found_l;
+}
+// The light sample's contribution once its ray is known to end on a light-material surface (pt.rs:191-218): the emission
+// of THAT surface towards the ray, times the light-side cosine (quirk Q14).
+__device__ __forceinline__ void shadow_light_contribution(const DevScene &S, float3 o, float3 d, const TraceHit &th, float pre, float lambda, uint32_t slot,
+                                                          float *__restrict__ acc) {
+  SurfaceHit sh;
+  reconstruct_hit(S, o, d, th, sh);
+  if (RPT_MAT_IS_LIGHT(sh.material)) {
+    Frame lf = frame_from_normal(sh.n);
+    float3 lwi = to_local(lf, -d);
+    float le = material_emission(S, S.materials[RPT_MAT_INDEX(sh.material)], lambda, lwi);
+    float v = pre * fabsf(lwi.z) * le;
+#ifdef RPT_DEBUG
+    if (slot == RPT_DEBUG_SLOT) printf("[shadow] hit inst=%u prim=%u t=%.7g le=%.7g lwi.z=%.7g pre=%.7g -> %.7g\n", th.inst, th.prim, th.t, le, lwi.z, pre, v);
+#endif
+    if (v != 0.0f) atomicAdd(acc + slot, v);
+  }
+}
+
 // NEE visibility. Light samples: closest hit, accepted when ANY light-material surface is hit, whose own
 // emission is used (pt.rs:177-218, F9). Environment samples: any hit kills the sample (pt.rs:254-263).
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
                                                           const uint32_t *__restrict__ sh_c, uint32_t *__restrict__ counts,
                                                           float *__restrict__ acc, unsigned long long *__restrict__ work) {
   extern __shared__ int s_stack[];
+  constexpr bool SMALL = MODE == TRAV_SMALL;
+  const float4 *s_tris = reinterpret_cast<const float4 *>(s_stack);
+  if (SMALL) stage_small_tris(S, reinterpret_cast<float4 *>(s_stack));
   TraceWork tw{0, 0, 0};
   const uint32_t n = counts[Q_SHADOW];
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_tiles = (n + 31u) >> 5;
+  // SMALL: every lane of the warp walks the leaf list together (SmallTrav), so lanes without a ray stay in the body with
+  // active == false instead of returning early.
   auto body = [&](uint32_t i) {
-    if (i >= n) return;
-    uint32_t c = __ldg(sh_c + i);
-    if (c == RPT_NONE) return;  // chunk padding
-    float4 a = __ldg(sh_a + i), b = __ldg(sh_b + i);
+    bool active = i < n;
+    uint32_t c = active ? __ldg(sh_c + i) : RPT_NONE;
+    active = active && c != RPT_NONE;  // chunk padding
+    if (!SMALL && !active) return;
+    float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 1, 0);
+    if (active) {
+      a = __ldg(sh_a + i);
+      b = __ldg(sh_b + i);
+    }
     float3 o = f3(a), d = f3(b);
     float pre = a.w, lambda = b.w;
     uint32_t slot = c & 0x7FFFFFFFu;
     TraceHit th;
-    if (c & 0x80000000u) {
-      if (!trace_ray<true>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) atomicAdd(acc + slot, pre);
+    const bool env_ray = active && (c & 0x80000000u);
+    if (SMALL) {
+      // environment samples (any hit kills the sample) and light samples share one walk of the leaf list: a light
+      // sample first finds the closest light-material shape (phase A below), then both kinds look for ANY leaf that
+      // beats what they hold (nothing / that light).
+      SmallTrav sv;
+      sv.init(RPT_INF);
+      bool search = active;
+      uint64_t key_l = 0;
+      float tl = RPT_INF;
+      if (S.num_light_geom) {
+        if (active && !env_ray) {
+          uint32_t inst_l = RPT_NONE;
+          bool found_l = shadow_closest_light<STATS>(S, o, d, tl, key_l, inst_l, tw);
+          search = found_l;  // no light along the ray: nothing to add
+          sv.closest = tl;
+          sv.best_key = key_l;
+          sv.found = found_l;
+          sv.out.t = tl;
+          sv.out.inst = inst_l;
+          sv.out.prim = 0;
+        }
+        sv.template run<true, STATS>(S, s_tris, o, d, RPT_INF, search, tw);
+      } else {
+        // light-material geometry is not a short analytic list: closest hit for light samples, any hit for environment
+        // samples; the two kinds are walked separately so that each loop stays warp-uniform
+        sv.template run<true, STATS>(S, s_tris, o, d, RPT_INF, env_ray, tw);
+        SmallTrav sl;
+        sl.init(RPT_INF);
+        sl.template run<false, STATS>(S, s_tris, o, d, RPT_INF, active && !env_ray, tw);
+        if (active && !env_ray) sv = sl;
+      }
+      if (!active) return;
+      if (env_ray) {
+        if (!sv.found) atomicAdd(acc + slot, pre);
+        return;
+      }
+      bool lit = S.num_light_geom ? (search && sv.best_key == key_l && sv.closest == tl) : sv.found;
+      if (lit) shadow_light_contribution(S, o, d, sv.out, pre, lambda, slot, acc);
+      return;
+    }
+    if (env_ray) {
+      if (!trace_ray<true, STATS>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) atomicAdd(acc + slot, pre);
       return;
     }
     bool lit;
@@ -799,72 +934,24 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
       // (A) the closest hit among the few light-material shapes, (B) ANY hit of the scene in front of it.
       float tl = RPT_INF;
       uint64_t key_l = 0;
-      bool found_l = false;
       uint32_t inst_l = RPT_NONE;
-      for (uint32_t k = 0; k < S.num_light_geom; ++k) {
-        uint32_t li = __ldg(S.light_geom + k);
-        const DevInstance &I = S.instances[li];
-        uint32_t flags = I.flags;
-        if ((flags & DI_KIND_MASK) == RPT_AGG_DISK) {
-          // A disk's bounding box is SMALLER than the disk (disk.rs:23-28: half extent radius / 2), so the part of the
-          // disk outside it is unreachable through the reference's BVH; the traversal reproduces that through the leaf
-          // box, phase A has to gate on the same box.
-          const float *bx = S.light_geom_box + 6 * k;
-          float3 winv, woinv;
-          slab_recip(o, d, winv, woinv);
-          float tn;
-          if (!slab_test(f3(__ldg(bx), __ldg(bx + 1), __ldg(bx + 2)), f3(__ldg(bx + 3), __ldg(bx + 4), __ldg(bx + 5)), woinv, winv, tl, tn)) continue;
-        }
-        float3 lo = o, ld = d;
-        if (flags & DI_HAS_TRANSFORM) {
-          lo = xform_point(I.rev, o);
-          ld = xform_vec(I.rev, d);
-        }
-        uint32_t kind = flags & DI_KIND_MASK;
-        float t;
-        bool hit = kind == RPT_AGG_RECT ? rect_test(I, lo, ld, 0.0f, tl, RPT_INF, t)
-                                        : (kind == RPT_AGG_SPHERE ? sphere_test(I, lo, ld, 0.0f, tl, RPT_INF, t) : disk_test(I, lo, ld, 0.0f, tl, RPT_INF, t));
-        RPT_STAT(tw.insts++);
-        if (hit) {
-          uint64_t key = tie_key(kind == RPT_AGG_SPHERE, I.order, 0);
-          if (!found_l || t < tl || key > key_l) {
-            tl = t;
-            key_l = key;
-            found_l = true;
-            inst_l = li;
-          }
-        }
-      }
-      if (!found_l) return;  // no light along the ray: nothing to add
+      if (!shadow_closest_light<STATS>(S, o, d, tl, key_l, inst_l, tw)) return;  // no light along the ray: nothing to add
       Trav tv;
       tv.init(S, o, d, RPT_INF);
       tv.closest = tl;  // only geometry that beats the light (closer, or equal t with a winning tie key) is accepted
       tv.best_key = key_l;
       tv.found = true;
-      tv.template run<true>(S, s_stack + threadIdx.x, TRACE_THREADS, tw);
+      tv.template run<true, STATS>(S, s_stack + threadIdx.x, TRACE_THREADS, tw);
       lit = tv.best_key == key_l && tv.closest == tl;
       th.t = tl;
       th.inst = inst_l;
       th.prim = 0;
     } else {
-      lit = trace_ray<false>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+      lit = trace_ray<false, STATS>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
     }
-    if (lit) {
-      SurfaceHit sh;
-      reconstruct_hit(S, o, d, th, sh);
-      if (RPT_MAT_IS_LIGHT(sh.material)) {
-        Frame lf = frame_from_normal(sh.n);
-        float3 lwi = to_local(lf, -d);
-        float le = material_emission(S, S.materials[RPT_MAT_INDEX(sh.material)], lambda, lwi);
-        float v = pre * fabsf(lwi.z) * le;
-#ifdef RPT_DEBUG
-        if (slot == RPT_DEBUG_SLOT) printf("[shadow] hit inst=%u prim=%u t=%.7g le=%.7g lwi.z=%.7g pre=%.7g -> %.7g\n", th.inst, th.prim, th.t, le, lwi.z, pre, v);
-#endif
-        if (v != 0.0f) atomicAdd(acc + slot, v);
-      }
-    }
+    if (lit) shadow_light_contribution(S, o, d, th, pre, lambda, slot, acc);
   };
-  if (!TRACE_DYNAMIC) {
+  if (!TRACE_DYNAMIC && !SMALL) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) body(i);
   } else {
@@ -872,7 +959,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
     ts.init(counts + F_SHADOW, n_tiles, gridDim.x * (TRACE_THREADS / 32), S.min_grab);
     for (uint32_t tile = ts.next(); tile != RPT_NONE; tile = ts.next()) body(tile * 32u + lane);
   }
-  flush_work(tw, work);
+  if (STATS) flush_work(tw, work);
 }
 
 // XYZColor::from(SingleWavelength) (pt.rs:614) + per-pixel accumulation (tiled.rs:390).
@@ -1127,22 +1214,74 @@ __global__ void __launch_bounds__(256) k_out_map(const float4 *__restrict__ film
   }
 }
 
+// ---- bandwidth probes (rpt_probe_bandwidth): the denominators of the roofline fractions, measured on the box ------------
+// mode 0: streaming 128-bit reads of the whole buffer, every repetition (buffer <= L2: L2 bandwidth; >> L2: HBM read bandwidth)
+// mode 1: copy first half -> second half (read + write bytes counted)
+// mode 2: dependent-free random 64-byte record gathers (4 x 16 B per lane, the BVH node fetch pattern) within the buffer
+__global__ void __launch_bounds__(256) k_probe_bw(const float4 *__restrict__ src, float4 *__restrict__ dst, uint64_t n16, uint32_t reps, int mode,
+                                                  float *__restrict__ sink) {
+  float acc = 0.0f;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+  if (mode == 0) {
+    for (uint32_t r = 0; r < reps; ++r)
+      for (uint64_t i = tid; i < n16; i += stride) {
+        float4 v;
+        asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i));  // L2-coherent: bypass L1
+        acc += v.x + v.y + v.z + v.w;
+      }
+  } else if (mode == 1) {
+    const uint64_t half = n16 / 2;
+    for (uint32_t r = 0; r < reps; ++r)
+      for (uint64_t i = tid; i < half; i += stride) dst[half + i] = src[i];
+  } else {
+    const uint64_t nrec = n16 / 4;
+    uint64_t x = tid * 0x9E3779B97F4A7C15ull + 12345u;
+    for (uint32_t r = 0; r < reps; ++r)
+      for (uint64_t i = tid; i < nrec; i += stride) {
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        const float4 *p = src + 4 * ((x >> 20) % nrec);
+        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+        acc += a.x + b.y + c.z + d.w;
+      }
+  }
+  if (acc == 123.456f) *sink = acc;  // keeps the loads alive
+}
+
 // generic closest-hit query of host-provided rays (rpt_trace_rays)
+template <int MODE>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32_t n, const float *__restrict__ o, const float *__restrict__ d,
                                                               const float *__restrict__ tmax, HitRec *__restrict__ hits) {
   extern __shared__ int s_stack[];
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  if (MODE == TRAV_SMALL) stage_small_tris(S, reinterpret_cast<float4 *>(s_stack));
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t n_round = (n + 31u) & ~31u;  // whole warps stay in the loop (TRAV_SMALL walks the leaf list warp-wide)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool active = i < n;
     TraceHit th;
     TraceWork tw{0, 0, 0};
-    trace_ray<false>(S, f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), tmax[i], s_stack + threadIdx.x,
-                     TRACE_THREADS, th, tw);
-    HitRec h;
-    h.t = th.t;
-    h.inst = th.inst;
-    h.prim = th.prim;
-    h.pad = 0;
-    hits[i] = h;
+    float3 ro = f3(0, 0, 0), rd = f3(0, 0, 1);
+    float tm = RPT_INF;
+    if (active) {
+      ro = f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+      rd = f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+      tm = tmax[i];
+    }
+    if (MODE == TRAV_SMALL) {
+      SmallTrav sv;
+      sv.init(tm);
+      sv.template run<false, false>(S, reinterpret_cast<const float4 *>(s_stack), ro, rd, tm, active, tw);
+      th = sv.out;
+    } else if (active) {
+      trace_ray<false, false>(S, ro, rd, tm, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+    }
+    if (active) {
+      HitRec h;
+      h.t = th.t;
+      h.inst = th.inst;
+      h.prim = th.prim;
+      h.pad = 0;
+      hits[i] = h;
+    }
   }
 }
 
@@ -1174,12 +1313,13 @@ struct DeviceBuffers {
     }
     size_t at = (block_used + 255) & ~(size_t)255;
     if (!block || at + bytes > block_size) {
-      void *p = spare(device);
-      if (p) {
+      void *p = nullptr;
+      {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        p = spare(device);
         spare(device) = nullptr;
-      } else {
-        CUDA_TRY(cudaMalloc(&p, kBlock));
       }
+      if (!p) CUDA_TRY(cudaMalloc(&p, kBlock));
       ptrs.push_back(p);
       block = static_cast<char *>(p);
       block_size = kBlock;
@@ -1202,9 +1342,12 @@ struct DeviceBuffers {
   void release() {
     for (void *p : ptrs) {
       if (!p) continue;
-      if (p == block && block_size == kBlock && !spare(device)) {
-        spare(device) = p;  // keep one standard block per device for the next scene
-        continue;
+      if (p == block && block_size == kBlock) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (!spare(device)) {
+          spare(device) = p;  // keep one standard block per device for the next scene
+          continue;
+        }
       }
       cudaFree(p);
     }
@@ -1235,7 +1378,9 @@ struct RptScene {
   size_t stack_smem = 0;
   uint32_t env_stack_count = 0;  // textures in the environment's stack (HDR)
   bool has_ggx = true;     // any material of the GGX class (else its shade kernel is never launched)
-  bool tma_tiles = false;  // k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
+  int trav_mode = TRAV_BVH;  // TRAV_SMALL for scenes of <= RPT_SMALL_MAX leaves without a BLAS (RPT_NO_SMALL=1 keeps the BVH);
+                             // TRAV_BVH_TMA: k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
+  size_t counts_cap = 0;     // bounces the per-bounce counter block has room for
   // timing of the last render
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -1302,9 +1447,11 @@ int occupancy_grid(K kernel, int threads, size_t smem, int num_sms) {
 
 // One set of wave buffers per device is kept alive across scenes: a host that creates a scene, renders and
 // destroys it every frame (bench.py's e2e leg, the Rust shim) should not pay a multi-GB cudaMalloc each time.
+// The caches (this one and DeviceBuffers::spare) are process-global and the ABI invites multi-threaded hosts (thread-local
+// rpt_last_error, one host thread per device in rpt_multi_*): every access goes through g_cache_mu.
 struct WaveCache {
   WaveBuffers wave{};
-  size_t slots = 0, shadow = 0, acc = 0;
+  size_t slots = 0, shadow = 0, acc = 0, counts_cap = 0;
   bool valid = false;
   float4 *film = nullptr;  // one parked film buffer (same reason: no cudaMalloc / cudaFree in a steady frame loop)
   size_t film_pixels = 0;
@@ -1322,28 +1469,40 @@ void release_wave_buffers(WaveBuffers &w) {
   w = WaveBuffers{};
 }
 
-// Called at scene destruction: park the buffers in the device's cache (keeping the larger set).
-void park_wave(RptScene *S);
-
 int free_wave(RptScene *S) {
-  WaveBuffers &w = S->wave;
-  void *ptrs[] = {w.paths[0], w.paths[1], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.sh_a, w.sh_b, w.sh_c, w.acc, w.counts, w.work};
-  for (void *p : ptrs)
-    if (p) cudaFree(p);
-  w = WaveBuffers{};
-  S->wave_slots = S->wave_shadow = S->wave_acc = 0;
+  release_wave_buffers(S->wave);
+  S->wave_slots = S->wave_shadow = S->wave_acc = S->counts_cap = 0;
   return 0;
 }
 
-// Queue capacity for `valid` real entries: chunked appends pad at most 31 entries per chunk (128 or 256 entries)
-// plus one chunk per warp per bin per appending kernel at kernel end (two shade kernels share the next-path and
-// shadow queues: 2 x 3552 warps x 8 bins x 128 entries = 7.3 M).
-size_t queue_cap(size_t valid) { return valid + valid / 4 + ((size_t)16 << 20); }
+// Queue capacities for `valid` real entries, derived from the launch grids of the kernels that append (the
+// old fixed allowance was a heuristic nothing enforced). Chunked appends lose at most 31 entries of every chunk to an
+// overflow (a warp that cannot fit its <= 32 new entries pads the tail and takes a fresh chunk), and at kernel end every
+// warp abandons at most one chunk per queue (per bin for the binned shadow queue). The next-path and shadow queues are
+// appended to by both shade kernels (diffuse, ggx); the class lists by k_trace.
+size_t path_queue_cap(const RptScene *S, size_t valid) {
+  size_t shade_warps = ((size_t)S->grid[K_SHADE_DIFFUSE] + (size_t)S->grid[K_SHADE_GGX]) * (SHADE_THREADS / 32);
+  size_t trace_warps = (size_t)S->grid[K_TRACE] * (TRACE_THREADS / 32);
+  size_t tail = std::max(shade_warps, trace_warps) * QCHUNK;
+  return valid + (valid * 31 + (QCHUNK - 31) - 1) / (QCHUNK - 31) + tail + QCHUNK;
+}
+size_t shadow_queue_cap(const RptScene *S, size_t valid) {
+  size_t shade_warps = ((size_t)S->grid[K_SHADE_DIFFUSE] + (size_t)S->grid[K_SHADE_GGX]) * (SHADE_THREADS / 32);
+  size_t tail = shade_warps * NBINS * QCHUNK_BINNED;
+  return valid + (valid * 31 + (QCHUNK_BINNED - 31) - 1) / (QCHUNK_BINNED - 31) + tail + QCHUNK_BINNED;
+}
+constexpr size_t kPathSlotBytes = 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t);
+constexpr size_t kShadowSlotBytes = 2 * sizeof(float4) + sizeof(uint32_t);
+size_t wave_bytes(const RptScene *S, size_t slots, uint32_t light_samples) {
+  return path_queue_cap(S, slots) * kPathSlotBytes + shadow_queue_cap(S, slots * light_samples) * kShadowSlotBytes + slots * sizeof(float);
+}
 
+// Called at scene destruction: park the buffers in the device's cache (keeping the larger set).
 void park_wave(RptScene *S) {
   if (S->device < 0 || S->device >= 64 || !S->wave.paths[0]) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
   WaveCache &c = g_wave_cache[S->device];
-  if (c.valid && c.slots >= S->wave_slots && c.shadow >= S->wave_shadow && c.acc >= S->wave_acc) {
+  if (c.valid && c.slots >= S->wave_slots && c.shadow >= S->wave_shadow && c.acc >= S->wave_acc && c.counts_cap >= S->counts_cap) {
     free_wave(S);
     return;
   }
@@ -1352,34 +1511,39 @@ void park_wave(RptScene *S) {
   c.slots = S->wave_slots;
   c.shadow = S->wave_shadow;
   c.acc = S->wave_acc;
+  c.counts_cap = S->counts_cap;
   c.valid = true;
   S->wave = WaveBuffers{};
-  S->wave_slots = S->wave_shadow = S->wave_acc = 0;
+  S->wave_slots = S->wave_shadow = S->wave_acc = S->counts_cap = 0;
 }
 
-int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid) {
-  size_t pcap = queue_cap(slots), scap = queue_cap(shadow_valid);
-  if (pcap <= S->wave_slots && scap <= S->wave_shadow && slots <= S->wave_acc) return 0;
+// slots = camera samples in a wave; shadow_valid = NEE rays a bounce can emit; bounces = per-bounce counter rows needed
+int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid, size_t bounces) {
+  size_t pcap = path_queue_cap(S, slots), scap = shadow_queue_cap(S, shadow_valid);
+  if (pcap <= S->wave_slots && scap <= S->wave_shadow && slots <= S->wave_acc && bounces <= S->counts_cap) return 0;
   free_wave(S);
   if (S->device >= 0 && S->device < 64) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
     WaveCache &c = g_wave_cache[S->device];
-    if (c.valid && pcap <= c.slots && scap <= c.shadow && slots <= c.acc) {
+    if (c.valid && pcap <= c.slots && scap <= c.shadow && slots <= c.acc && bounces <= c.counts_cap) {
       S->wave = c.wave;
       S->wave_slots = c.slots;
       S->wave_shadow = c.shadow;
       S->wave_acc = c.acc;
+      S->counts_cap = c.counts_cap;
       c.wave = WaveBuffers{};
-      c.slots = c.shadow = c.acc = 0;
+      c.slots = c.shadow = c.acc = c.counts_cap = 0;
       c.valid = false;
       return 0;
     }
     if (c.valid) {  // too small for this job: release it before allocating a bigger set
       release_wave_buffers(c.wave);
-      c.slots = c.shadow = c.acc = 0;
+      c.slots = c.shadow = c.acc = c.counts_cap = 0;
       c.valid = false;
     }
   }
   WaveBuffers &w = S->wave;
+  size_t ccap = std::max<size_t>(bounces, 64);
   CUDA_TRY(cudaMalloc(&w.paths[0], pcap * sizeof(PathRec)));
   CUDA_TRY(cudaMalloc(&w.paths[1], pcap * sizeof(PathRec)));
   CUDA_TRY(cudaMalloc(&w.hits, pcap * sizeof(HitRec)));
@@ -1390,24 +1554,20 @@ int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid) {
   CUDA_TRY(cudaMalloc(&w.sh_b, scap * sizeof(float4)));
   CUDA_TRY(cudaMalloc(&w.sh_c, scap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&w.acc, slots * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&w.counts, (RPT_MAX_BOUNCES + 1) * Q_COUNT * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.counts, (ccap + 1) * Q_COUNT * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&w.work, 6 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemset(w.work, 0, 6 * sizeof(unsigned long long)));
   S->wave_slots = pcap;
   S->wave_shadow = scap;
   S->wave_acc = slots;
+  S->counts_cap = ccap;
   return 0;
 }
 
-size_t bytes_per_slot(uint32_t light_samples) {
-  // path queues x2, hit, 3 class lists (all with the 1/8 padding allowance), energy, shadow records
-  size_t per_path = 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t);
-  size_t per_shadow = 2 * sizeof(float4) + sizeof(uint32_t);
-  return per_path + per_path / 4 + sizeof(float) + (size_t)light_samples * (per_shadow + per_shadow / 4);
-}
-
+// Per-kernel CUDA-event timing is a run-time opt-in (RPT_FLAG_KERNEL_TIMES): a plain render records two events in all.
 struct Launcher {
   RptScene *S;
+  bool timed;
   cudaEvent_t next_event() {
     if (S->ev_used == S->ev_pool.size()) {
       cudaEvent_t e;
@@ -1417,15 +1577,17 @@ struct Launcher {
     return S->ev_pool[S->ev_used++];
   }
   void begin(int kernel) {
+    S->kernel_launches[kernel] += 1;
+    if (!timed) return;
     size_t e0 = S->ev_used;
     cudaEventRecord(next_event(), S->stream);
     S->spans.push_back({kernel, e0, 0});
   }
   void end() {
+    if (!timed) return;
     size_t e1 = S->ev_used;
     cudaEventRecord(next_event(), S->stream);
     S->spans.back().e1 = e1;
-    S->kernel_launches[S->spans.back().kernel] += 1;
   }
 };
 
@@ -1433,8 +1595,8 @@ int validate(const RptScene *S, const RptRenderParams *P) {
   if (!S || !P) return fail("null argument");
   if (P->width == 0 || P->height == 0) return fail("empty film");
   if (P->camera >= S->cameras.size()) return fail("camera index out of range");
-  if (P->max_bounces > RPT_MAX_BOUNCES) return fail("max_bounces exceeds RPT_MAX_BOUNCES (64)");
-  if (P->light_samples > 8) return fail("light_samples > 8 is not supported by the shade kernel's shadow-record staging");
+  // max_bounces and light_samples are u16 in the reference (parsing/config.rs:22-23) and any value is accepted here too
+  if (P->max_bounces > 65535u || P->light_samples > 65535u) return fail("max_bounces / light_samples exceed the reference's u16 range (parsing/config.rs:22-23)");
   if ((uint64_t)P->width * P->height >= (1ull << 31)) return fail("film too large");
   return 0;
 }
@@ -1455,6 +1617,40 @@ RenderCtx make_ctx(const RptScene *S, const RptRenderParams *P) {
   return R;
 }
 
+// ---- kernel dispatch over the (traversal mode, statistics) template parameters
+template <bool RAYGEN>
+void launch_trace(RptScene *S, bool stats, const PathRec *in, uint32_t *cb, const RenderCtx &R, PathRec *paths_out) {
+  WaveBuffers &w = S->wave;
+#define RPT_TRACE_LAUNCH(MODE, STATS)                                                                                                         \
+  k_trace<MODE, RAYGEN, STATS><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, \
+                                                                                               w.work, w.acc, R, paths_out)
+  if (S->trav_mode == TRAV_SMALL) {
+    if (stats) RPT_TRACE_LAUNCH(TRAV_SMALL, true); else RPT_TRACE_LAUNCH(TRAV_SMALL, false);
+  } else {
+    if (stats) RPT_TRACE_LAUNCH(TRAV_BVH, true); else RPT_TRACE_LAUNCH(TRAV_BVH, false);
+  }
+#undef RPT_TRACE_LAUNCH
+}
+void launch_trace_tma(RptScene *S, bool stats, const PathRec *in, uint32_t *cb) {
+  WaveBuffers &w = S->wave;
+  RenderCtx R{};
+  if (stats)
+    k_trace<TRAV_BVH_TMA, false, true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc, R, nullptr);
+  else
+    k_trace<TRAV_BVH_TMA, false, false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc, R, nullptr);
+}
+void launch_shadow(RptScene *S, bool stats, uint32_t *cb) {
+  WaveBuffers &w = S->wave;
+#define RPT_SHADOW_LAUNCH(MODE, STATS) \
+  k_shadow<MODE, STATS><<<S->grid[K_SHADOW], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc, w.work + 3)
+  if (S->trav_mode == TRAV_SMALL) {
+    if (stats) RPT_SHADOW_LAUNCH(TRAV_SMALL, true); else RPT_SHADOW_LAUNCH(TRAV_SMALL, false);
+  } else {
+    if (stats) RPT_SHADOW_LAUNCH(TRAV_BVH, true); else RPT_SHADOW_LAUNCH(TRAV_BVH, false);
+  }
+#undef RPT_SHADOW_LAUNCH
+}
+
 // Renders P->spp samples per pixel into S->film (un-normalised sum). Fills counters.
 int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   if (int rc = validate(S, P)) return rc;
@@ -1463,77 +1659,97 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   if (S->film_pixels != wh) {
     if (S->film) cudaFree(S->film);
     S->film = nullptr;
-    WaveCache &fc = g_wave_cache[S->device & 63];
-    if (fc.film && fc.film_pixels == wh) {
-      S->film = fc.film;
-      fc.film = nullptr;
-      fc.film_pixels = 0;
-    } else {
-      CUDA_TRY(cudaMalloc(&S->film, wh * sizeof(float4)));
+    {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      WaveCache &fc = g_wave_cache[S->device & 63];
+      if (fc.film && fc.film_pixels == wh) {
+        S->film = fc.film;
+        fc.film = nullptr;
+        fc.film_pixels = 0;
+      }
     }
+    if (!S->film) CUDA_TRY(cudaMalloc(&S->film, wh * sizeof(float4)));
     S->film_pixels = wh;
   }
   CUDA_TRY(cudaMemsetAsync(S->film, 0, wh * sizeof(float4), S->stream));
+  const bool stats = (P->flags & RPT_FLAG_BVH_STATS) != 0;
+  const uint32_t max_bounces = P->only_direct ? 1u : P->max_bounces;
 
   // wave sizing: as many spp per wave as fit the memory budget and the 30-bit slot id. When the buffers this
   // scene already holds fit the whole job, skip the (slow) memory query: a steady-state frame loop allocates nothing.
   uint32_t spp_chunk;
   size_t want_slots = wh * (size_t)std::max<uint32_t>(P->spp, 1);
-  if (want_slots < ((size_t)1 << 30) && queue_cap(want_slots) <= S->wave_slots && queue_cap(want_slots * P->light_samples) <= S->wave_shadow &&
-      want_slots <= S->wave_acc) {
+  if (want_slots < ((size_t)1 << 30) && path_queue_cap(S, want_slots) <= S->wave_slots &&
+      shadow_queue_cap(S, want_slots * P->light_samples) <= S->wave_shadow && want_slots <= S->wave_acc && max_bounces <= S->counts_cap) {
     spp_chunk = std::max<uint32_t>(P->spp, 1);
   } else {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    size_t held = S->wave_acc * bytes_per_slot(0) + S->wave_shadow * (2 * sizeof(float4) + sizeof(uint32_t));
-    if (S->device >= 0 && S->device < 64 && g_wave_cache[S->device].valid)
-      held += g_wave_cache[S->device].acc * bytes_per_slot(0) + g_wave_cache[S->device].shadow * (2 * sizeof(float4) + sizeof(uint32_t));
+    size_t held = S->wave_slots * kPathSlotBytes + S->wave_shadow * kShadowSlotBytes + S->wave_acc * sizeof(float);
+    if (S->device >= 0 && S->device < 64) {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      const WaveCache &c = g_wave_cache[S->device];
+      if (c.valid) held += c.slots * kPathSlotBytes + c.shadow * kShadowSlotBytes + c.acc * sizeof(float);
+    }
     size_t budget = std::min<size_t>((size_t)((free_b + held) * 0.5), (size_t)32 << 30);
-    size_t per_slot = bytes_per_slot(P->light_samples);
-    size_t max_slots = std::min<size_t>(budget / per_slot, (size_t)1 << 30);
+    // the queue capacities are affine in the slot count: fixed part (end-of-kernel chunk tails) + per-slot part
+    size_t fixed = wave_bytes(S, 0, P->light_samples);
+    size_t per_1k = wave_bytes(S, 1024, P->light_samples) - fixed;
+    if (budget <= fixed) return fail("not enough device memory for the wave queues");
+    size_t max_slots = std::min<size_t>((budget - fixed) / per_1k * 1024, (size_t)1 << 30);
     if (wh > max_slots) return fail("film does not fit one wave");
     spp_chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(P->spp ? P->spp : 1, max_slots / wh));
   }
   size_t slots = wh * spp_chunk;
-  if (int rc = ensure_wave(S, slots, slots * P->light_samples)) return rc;
+  if (int rc = ensure_wave(S, slots, slots * P->light_samples, max_bounces)) return rc;
 
   S->ev_used = 0;
   S->spans.clear();
   std::memset(S->kernel_ms, 0, sizeof(S->kernel_ms));
   std::memset(S->kernel_launches, 0, sizeof(S->kernel_launches));
-  Launcher T{S};
+  Launcher T{S, (P->flags & RPT_FLAG_KERNEL_TIMES) != 0};
   RenderCtx R = make_ctx(S, P);
-  const uint32_t max_bounces = P->only_direct ? 1u : P->max_bounces;
   WaveBuffers &w = S->wave;
-  std::vector<uint32_t> h_counts((RPT_MAX_BOUNCES + 1) * Q_COUNT);
+  const size_t n_counts = ((size_t)max_bounces + 1) * Q_COUNT;
+  std::vector<uint32_t> h_counts(n_counts);
   RptCounters C{};
   size_t film_smem = 3 * (size_t)S->dev.num_lambda * sizeof(float);
 
-  CUDA_TRY(cudaMemsetAsync(w.work, 0, 6 * sizeof(unsigned long long), S->stream));
+  if (stats) CUDA_TRY(cudaMemsetAsync(w.work, 0, 6 * sizeof(unsigned long long), S->stream));
   size_t ev_first = S->ev_used;
   cudaEventRecord(T.next_event(), S->stream);
   for (uint32_t done = 0; done < P->spp; done += spp_chunk) {
     uint32_t chunk = std::min(spp_chunk, P->spp - done);
     R.n_slots = (uint32_t)(wh * chunk);
     R.sample_base = P->spp_offset + done;
-    CUDA_TRY(cudaMemsetAsync(w.counts, 0, h_counts.size() * sizeof(uint32_t), S->stream));
+    CUDA_TRY(cudaMemsetAsync(w.counts, 0, n_counts * sizeof(uint32_t), S->stream));
     CUDA_TRY(cudaMemsetAsync(w.acc, 0, (size_t)R.n_slots * sizeof(float), S->stream));
-    const bool fused_raygen = !S->tma_tiles;  // bounce 0's k_trace generates the camera vertices itself
-    if (!fused_raygen) {
+    const bool tma = S->trav_mode == TRAV_BVH_TMA;
+    if (tma) {  // (the other modes generate the camera vertices inside bounce 0's k_trace)
       T.begin(K_RAYGEN);
       k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
       T.end();
     }
+    uint32_t bounces_run = 0;
     for (uint32_t b = 0; b < max_bounces; ++b) {
+      // Long walks (the reference accepts max_bounces up to 65535): once past 16 bounces, look at the path count every 8
+      // bounces and stop launching when the wave has died out (russian roulette empties it long before).
+      if (b >= 16 && (b & 7u) == 0) {
+        uint32_t alive = 0;
+        CUDA_TRY(cudaMemcpyAsync(&alive, w.counts + (size_t)b * Q_COUNT + N_PATHS, sizeof(uint32_t), cudaMemcpyDeviceToHost, S->stream));
+        CUDA_TRY(cudaStreamSynchronize(S->stream));
+        if (alive == 0) break;
+      }
+      bounces_run = b + 1;
       uint32_t *cb = w.counts + (size_t)b * Q_COUNT, *cn = w.counts + (size_t)(b + 1) * Q_COUNT;
       PathRec *in = w.paths[b & 1], *out = w.paths[(b + 1) & 1];
       T.begin(K_TRACE);
-      if (S->tma_tiles)
-        k_trace<true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc);
-      else if (b == 0 && fused_raygen)
-        k_trace<false, true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, nullptr, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc, R, in);
+      if (tma)
+        launch_trace_tma(S, stats, in, cb);
+      else if (b == 0)
+        launch_trace<true>(S, stats, nullptr, cb, R, in);
       else
-        k_trace<false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc);
+        launch_trace<false>(S, stats, in, cb, R, nullptr);
       T.end();
       if (S->dev.env_kind != RPT_ENV_CONSTANT) {  // (a Constant environment's vertices are finished inside k_trace)
         T.begin(K_SHADE_MISS);
@@ -1550,20 +1766,20 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       }
       if (P->light_samples > 0) {
         T.begin(K_SHADOW);
-        k_shadow<<<S->grid[K_SHADOW], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc, w.work + 3);
+        launch_shadow(S, stats, cb);
         T.end();
       }
     }
     T.begin(K_FILM);
     k_film<<<S->grid[K_FILM], 256, film_smem, S->stream>>>(S->dev, R, w.acc, S->film);
     T.end();
-    CUDA_TRY(cudaMemcpyAsync(h_counts.data(), w.counts, h_counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, S->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_counts.data(), w.counts, n_counts * sizeof(uint32_t), cudaMemcpyDeviceToHost, S->stream));
     CUDA_TRY(cudaStreamSynchronize(S->stream));
     CUDA_TRY(cudaGetLastError());
     // Profile counters (profile.rs:1-8) from the queue sizes
     C.camera_rays += R.n_slots;
     C.bounce_rays += R.n_slots;  // the camera vertex (pt.rs:465, integrator/utils.rs:375)
-    for (uint32_t b = 0; b < max_bounces; ++b) {
+    for (uint32_t b = 0; b < bounces_run; ++b) {
       const uint32_t *c = &h_counts[(size_t)b * Q_COUNT];
       C.segments += c[N_PATHS];
       C.true_rays += c[N_PATHS] + c[N_SHADOW];
@@ -1575,8 +1791,8 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   }
   size_t ev_last = S->ev_used;
   cudaEventRecord(T.next_event(), S->stream);
-  unsigned long long h_work[6];
-  CUDA_TRY(cudaMemcpyAsync(h_work, w.work, sizeof(h_work), cudaMemcpyDeviceToHost, S->stream));
+  unsigned long long h_work[6] = {0, 0, 0, 0, 0, 0};
+  if (stats) CUDA_TRY(cudaMemcpyAsync(h_work, w.work, sizeof(h_work), cudaMemcpyDeviceToHost, S->stream));
   CUDA_TRY(cudaStreamSynchronize(S->stream));
   C.walk_nodes = h_work[0];
   C.walk_tris = h_work[1];
@@ -1620,16 +1836,21 @@ int rpt_scene_destroy(RptScene *S) {
   cudaSetDevice(S->device);
   park_wave(S);
   if (S->film) {
-    WaveCache &fc = g_wave_cache[S->device & 63];
-    if (!fc.film) {
-      fc.film = S->film;
-      fc.film_pixels = S->film_pixels;
-    } else {
-      cudaFree(S->film);
+    bool parked = false;
+    {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      WaveCache &fc = g_wave_cache[S->device & 63];
+      if (!fc.film) {
+        fc.film = S->film;
+        fc.film_pixels = S->film_pixels;
+        parked = true;
+      }
     }
+    if (!parked) cudaFree(S->film);
   }
   S->bufs.release();
   {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
     WaveCache &sc = g_wave_cache[S->device & 63];
     if (S->stream && !sc.stream) {  // (every entry point leaves the stream idle: nothing is pending on it)
       sc.stream = S->stream;
@@ -1671,15 +1892,15 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   };
   lap("device properties");
   {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
     WaveCache &sc = g_wave_cache[device & 63];
     if (sc.stream) {
       S->stream = sc.stream;
       S->ev_pool.swap(sc.events);
       sc.stream = nullptr;
-    } else if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) != cudaSuccess) {
-      return bail(fail("cudaStreamCreate failed"));
     }
   }
+  if (!S->stream && cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
   lap("stream create");
 
   // ---- geometry: per-mesh BLAS, then the TLAS over instance boxes
@@ -1824,6 +2045,41 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   S->stack_entries = need <= 16 ? 16 : (need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 0)));
   if (S->stack_entries == 0) return bail(fail("BVH deeper than the largest traversal stack (128 entries)"));
   S->stack_smem = (size_t)S->stack_entries * TRACE_THREADS * sizeof(int);
+  // Small-scene mode: every leaf is a triangle in world space or an analytic instance, and there are few of them.
+  std::vector<float4> small_tris;
+  std::vector<uint4> small_leaves;
+  std::vector<float> small_boxes;
+  uint32_t small_ntri = 0;
+  {
+    const char *e = std::getenv("RPT_NO_SMALL");
+    const bool allow = !(e && e[0] == '1');
+    if (allow && needed_blas_depth == 0 && leaves.size() <= RPT_SMALL_MAX) {
+      for (int pass = 0; pass < 2; ++pass)  // triangles first, then whole instances
+        for (size_t l = 0; l < leaves.size(); ++l) {
+          const uint4 &lf = leaves[l];
+          const bool is_tri = lf.y != RPT_NONE;
+          if (is_tri != (pass == 0)) continue;
+          if (is_tri) {
+            const float4 *tv = &tri_verts[3 * (size_t)lf.z];
+            uint32_t tri_order;
+            std::memcpy(&tri_order, &tv[1].w, 4);
+            small_leaves.push_back(make_uint4(lf.x, lf.y, tri_order, lf.w));
+            for (int kz = 0; kz < 3; ++kz)  // tri_shuffle(v, kz): kz 0 -> (y, z, x), 1 -> (z, x, y), 2 -> (x, y, z)
+              for (int v = 0; v < 3; ++v) {
+                const float4 &q = tv[v];
+                small_tris.push_back(kz == 0 ? make_float4(q.y, q.z, q.x, 0.0f) : (kz == 1 ? make_float4(q.z, q.x, q.y, 0.0f) : make_float4(q.x, q.y, q.z, 0.0f)));
+              }
+            ++small_ntri;
+          } else {
+            small_leaves.push_back(make_uint4(lf.x, RPT_NONE, 0u, lf.w));
+            small_boxes.insert(small_boxes.end(), leaf_box[l].mn, leaf_box[l].mn + 3);
+            small_boxes.insert(small_boxes.end(), leaf_box[l].mx, leaf_box[l].mx + 3);
+          }
+        }
+      S->trav_mode = TRAV_SMALL;
+      S->stack_smem = std::max<size_t>(16, small_tris.size() * sizeof(float4));
+    }
+  }
   for (auto &hn : tlas.nodes) nodes.push_back(to_dev_node(hn, 0));
   S->stats.tlas_nodes = tlas.nodes.size();
   std::vector<int32_t> mesh_root(d->num_meshes);
@@ -1895,6 +2151,11 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   rc |= B.upload(d->lights, d->num_lights, &D.lights);
   rc |= B.upload(light_geom.data(), light_geom.size(), &D.light_geom);
   rc |= B.upload(light_geom_box.data(), light_geom_box.size(), &D.light_geom_box);
+  rc |= B.upload(small_tris.data(), small_tris.size(), &D.small_tris);
+  rc |= B.upload(small_leaves.data(), small_leaves.size(), &D.small_leaves);
+  rc |= B.upload(small_boxes.data(), small_boxes.size(), &D.small_boxes);
+  D.small_n = S->trav_mode == TRAV_SMALL ? (uint32_t)small_leaves.size() : 0u;
+  D.small_ntri = small_ntri;
   D.num_light_geom = (uint32_t)light_geom.size();
   rc |= B.upload(d->materials, d->num_materials, &D.materials);
   S->has_ggx = false;
@@ -1964,27 +2225,41 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   lap("uploads");
   size_t film_smem = 3 * (size_t)d->num_lambda * sizeof(float);
   if (film_smem > 48 * 1024) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
     if (cudaFuncSetAttribute(k_film, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)film_smem) != cudaSuccess)
       return bail(fail("num_lambda too large for the film kernel's shared-memory CIE tables"));
   }
   S->grid[K_RAYGEN] = occupancy_grid(k_raygen, 256, 0, S->num_sms);
-  if (S->stack_smem > 48 * 1024) {
-    cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
-    cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
-    cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
-    cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
-    cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->stack_smem);
-  }
   {
     const char *e = std::getenv("RPT_TMA_TILES");
-    S->tma_tiles = e && e[0] == '1';
+    if (e && e[0] == '1' && S->trav_mode == TRAV_BVH) S->trav_mode = TRAV_BVH_TMA;
   }
-  S->grid[K_TRACE] = S->tma_tiles ? occupancy_grid(k_trace<true>, TRACE_THREADS, S->stack_smem, S->num_sms)
-                                  : occupancy_grid(k_trace<false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+  if (S->stack_smem > 48 * 1024) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    const int sm = (int)S->stack_smem;
+    cudaFuncSetAttribute(k_trace<TRAV_BVH, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_TMA, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_TMA, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_shadow<TRAV_BVH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_shadow<TRAV_BVH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace_rays<TRAV_BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  }
+  if (S->trav_mode == TRAV_SMALL) {
+    S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_SMALL, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+    S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_SMALL, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+  } else if (S->trav_mode == TRAV_BVH_TMA) {
+    S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH_TMA, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+    S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+  } else {
+    S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+    S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+  }
   S->grid[K_SHADE_MISS] = occupancy_grid(k_shade_miss, 256, 0, S->num_sms);
   S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_surface<Q_DIFFUSE>, SHADE_THREADS, 0, S->num_sms);
   S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_surface<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
-  S->grid[K_SHADOW] = occupancy_grid(k_shadow, TRACE_THREADS, S->stack_smem, S->num_sms);
   S->grid[K_FILM] = occupancy_grid(k_film, 256, film_smem, S->num_sms);
   lap("occupancy queries");
   *out = S;
@@ -2030,17 +2305,18 @@ int rpt_trace_primary(RptScene *S, const RptRenderParams *P, uint32_t *inst, uin
   if (!inst || !prim || !t) return fail("null argument");
   CUDA_TRY(cudaSetDevice(S->device));
   size_t wh = (size_t)P->width * P->height;
-  if (int rc = ensure_wave(S, wh, wh * P->light_samples)) return rc;
+  if (int rc = ensure_wave(S, wh, wh * P->light_samples, 1)) return rc;
   RenderCtx R = make_ctx(S, P);
   R.n_slots = (uint32_t)wh;
   R.sample_base = P->spp_offset;
   WaveBuffers &w = S->wave;
-  CUDA_TRY(cudaMemsetAsync(w.counts, 0, (RPT_MAX_BOUNCES + 1) * Q_COUNT * sizeof(uint32_t), S->stream));
-  k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
-  if (S->tma_tiles)
-    k_trace<true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts, w.work, w.acc);
-  else
-    k_trace<false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.paths[0], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.counts, w.work, w.acc);
+  CUDA_TRY(cudaMemsetAsync(w.counts, 0, 2 * Q_COUNT * sizeof(uint32_t), S->stream));
+  if (S->trav_mode == TRAV_BVH_TMA) {
+    k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
+    launch_trace_tma(S, false, w.paths[0], w.counts);
+  } else {
+    launch_trace<true>(S, false, nullptr, w.counts, R, w.paths[0]);
+  }
   std::vector<HitRec> h(wh);
   CUDA_TRY(cudaMemcpyAsync(h.data(), w.hits, wh * sizeof(HitRec), cudaMemcpyDeviceToHost, S->stream));
   CUDA_TRY(cudaStreamSynchronize(S->stream));
@@ -2066,7 +2342,10 @@ int rpt_trace_rays(RptScene *S, uint32_t n, const float *origins, const float *d
   CUDA_TRY(cudaMemcpyAsync(d_o, origins, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
   CUDA_TRY(cudaMemcpyAsync(d_d, dirs, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
   CUDA_TRY(cudaMemcpyAsync(d_t, tmax, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
-  k_trace_rays<<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
+  if (S->trav_mode == TRAV_SMALL)
+    k_trace_rays<TRAV_SMALL><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
+  else
+    k_trace_rays<TRAV_BVH><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
   std::vector<HitRec> h(n);
   CUDA_TRY(cudaMemcpyAsync(h.data(), d_h, (size_t)n * sizeof(HitRec), cudaMemcpyDeviceToHost, S->stream));
   CUDA_TRY(cudaStreamSynchronize(S->stream));
@@ -2214,6 +2493,40 @@ int rpt_scene_bake_importance_map(RptScene *S, const RptImapBake *B, float *row_
   D.imap_m_pdf = d_mpdf;
   D.imap_m_cdf = d_mcdf;
   if (marginal_integral) *marginal_integral = integral;
+  return 0;
+}
+
+int rpt_probe_bandwidth(int device, uint64_t bytes, uint32_t reps, int mode, double *gbps) {
+  if (!gbps || bytes < 4096 || reps == 0 || mode < 0 || mode > 2) return fail("bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  float4 *buf = nullptr;
+  float *sink = nullptr;
+  const uint64_t n16 = bytes / 16;
+  CUDA_TRY(cudaMalloc(&buf, n16 * 16));
+  CUDA_TRY(cudaMalloc(&sink, 4));
+  CUDA_TRY(cudaMemset(buf, 0, n16 * 16));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int it = 0; it < 5; ++it) {  // first iteration warms the L2; best of the rest
+    cudaEventRecord(e0);
+    k_probe_bw<<<sms * 8, 256>>>(buf, buf, n16, reps, mode, sink);
+    cudaEventRecord(e1);
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double moved = mode == 1 ? (double)(n16 / 2) * 32.0 * reps : (mode == 2 ? (double)(n16 / 4) * 64.0 * reps : (double)n16 * 16.0 * reps);
+    if (it > 0) best = std::max(best, moved / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(sink);
+  CUDA_TRY(cudaGetLastError());
+  *gbps = best;
   return 0;
 }
 

@@ -17,7 +17,7 @@ from . import curves as C
 from . import world as W
 
 F32 = np.float32
-ABI_VERSION = 7
+ABI_VERSION = 8
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "librpt_b200.so")
@@ -97,8 +97,12 @@ class RptRenderParams(ct.Structure):
     _fields_ = [
         ("width", c_u32), ("height", c_u32), ("spp", c_u32), ("spp_offset", c_u32), ("spp_total", c_u32),
         ("min_bounces", c_u32), ("max_bounces", c_u32), ("light_samples", c_u32), ("only_direct", c_u32),
-        ("lambda_lo", c_f), ("lambda_hi", c_f), ("camera", c_u32), ("seed", c_u64),
+        ("lambda_lo", c_f), ("lambda_hi", c_f), ("camera", c_u32), ("seed", c_u64), ("flags", c_u32), ("reserved", c_u32),
     ]
+
+
+FLAG_KERNEL_TIMES = 1  # RPT_FLAG_KERNEL_TIMES: CUDA events around every kernel launch -> Scene.kernel_times()
+FLAG_BVH_STATS = 2     # RPT_FLAG_BVH_STATS: RptCounters.walk_* / shadow_* are filled
 
 
 class RptCounters(ct.Structure):
@@ -142,7 +146,7 @@ class RptSceneStats(ct.Structure):
 RPT_SYMBOLS = [
     "rpt_last_error", "rpt_abi_version", "rpt_device_count", "rpt_scene_create", "rpt_scene_destroy",
     "rpt_render_pt", "rpt_render_pt_device", "rpt_trace_primary", "rpt_trace_rays", "rpt_film_scale",
-    "rpt_last_kernel_times", "rpt_scene_stats", "rpt_output_film", "rpt_scene_bake_importance_map",
+    "rpt_last_kernel_times", "rpt_scene_stats", "rpt_output_film", "rpt_scene_bake_importance_map", "rpt_probe_bandwidth",
 ]
 
 
@@ -197,6 +201,8 @@ def load_library(path: Optional[str] = None) -> ct.CDLL:
     lib.rpt_scene_stats.restype = ct.c_int
     lib.rpt_output_film.argtypes = [ct.c_void_p, ct.c_void_p, c_u32, c_u32, ct.POINTER(RptOutputSettings), ct.c_void_p, ct.c_void_p, ct.c_void_p]
     lib.rpt_output_film.restype = ct.c_int
+    lib.rpt_probe_bandwidth.argtypes = [ct.c_int, c_u64, c_u32, ct.c_int, ct.POINTER(ct.c_double)]
+    lib.rpt_probe_bandwidth.restype = ct.c_int
     if lib.rpt_abi_version() != ABI_VERSION:
         raise RptError(f"ABI mismatch: library {lib.rpt_abi_version()} vs binding {ABI_VERSION}; rebuild")
     if path is None:
@@ -330,6 +336,14 @@ class FlatScene:
         k.append(cams)
         d.num_cameras, d.cameras = len(world.cameras), cams
         self.desc = d
+
+
+def probe_bandwidth(lib: ct.CDLL, device: int, nbytes: int, reps: int, mode: int) -> float:
+    """rpt_probe_bandwidth -> GB/s (mode 0 streaming read, 1 copy, 2 random 64-byte gathers)."""
+    out = ct.c_double()
+    if lib.rpt_probe_bandwidth(device, nbytes, reps, mode, ct.byref(out)) != 0:
+        raise RptError(lib.rpt_last_error().decode("utf-8", "replace"))
+    return float(out.value)
 
 
 class Scene:

@@ -65,7 +65,7 @@ class PTSettings:
         d["wavelength_bounds"] = tuple(d["wavelength_bounds"])
         return PTSettings(**d)
 
-    def params(self, seed: int = 0, spp: Optional[int] = None, spp_offset: int = 0, spp_total: Optional[int] = None) -> ffi.RptRenderParams:
+    def params(self, seed: int = 0, spp: Optional[int] = None, spp_offset: int = 0, spp_total: Optional[int] = None, flags: int = 0) -> ffi.RptRenderParams:
         p = ffi.RptRenderParams()
         p.width, p.height = self.width, self.height
         p.spp = self.min_samples if spp is None else spp
@@ -76,6 +76,7 @@ class PTSettings:
         p.lambda_lo, p.lambda_hi = self.wavelength_bounds
         p.camera = self.camera
         p.seed = seed
+        p.flags = flags  # run-time instrumentation (ffi.FLAG_KERNEL_TIMES | ffi.FLAG_BVH_STATS); off by default
         return p
 
 

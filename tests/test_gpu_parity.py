@@ -470,10 +470,52 @@ def test_tma_tile_variant(monkeypatch):
     tma.close()
 
 
+@pytest.mark.parametrize("name", ["cornell", "test_nee_sphere", "rtiow2", "orb_caustic", "sun_test", "furnace", "hdri"])
+def test_small_scene_mode_equals_bvh(monkeypatch, name):
+    """Scenes of <= 64 leaves skip the BVH (warp-uniform walk of the leaf list out of shared memory, SmallTrav); RPT_NO_SMALL=1
+    keeps the BVH walk. Both answer the same query, so hit ids, counters and films are identical (energy atomics reorder)."""
+    world, st, flat = parity.load_scene(name, 160, 90, 4)
+    small = parity.cuda_scene(flat)
+    monkeypatch.setenv("RPT_NO_SMALL", "1")
+    bvh = parity.cuda_scene(flat)
+    monkeypatch.delenv("RPT_NO_SMALL")
+    p = st.params(seed=9, flags=2)
+    fs, cs_ = small.render_pt(p)
+    fb, cb = bvh.render_pt(p)
+    assert cs_.walk_nodes == 0 and cb.walk_nodes > 0, "the two scenes must really run the two modes"
+    for k in ("segments", "bounce_rays", "shadow_rays", "shadow_rays_traced", "env_hits"):
+        assert getattr(cs_, k) == getattr(cb, k), (name, k)
+    assert np.allclose(fs, fb, rtol=1e-5, atol=1e-9), (name, float(np.abs(fs - fb).max()))
+    gi, gp, gt = small.trace_primary(p)
+    bi, bp, bt = bvh.trace_primary(p)
+    assert np.array_equal(gi, bi) and np.array_equal(gp, bp) and np.array_equal(gt, bt)
+    small.close()
+    bvh.close()
+
+
+def test_reference_parameter_ranges(scenes):
+    """The reference takes any u16 for light_samples and max_bounces (parsing/config.rs:22-23); so does the library
+    (round 1 rejected light_samples > 8 and max_bounces > 64)."""
+    st, cs, os_ = scenes("cornell", 48, 27, 2)
+    p = st.params(seed=4)
+    p.light_samples, p.max_bounces = 11, 100
+    fg, cg = cs.render_pt(p)
+    fo, co = os_.render_pt(p)
+    assert cg.camera_rays == co.camera_rays and abs(cg.segments - co.segments) <= 4
+    assert parity.rel_mse(fg, fo) < 2e-3 and parity.mean_rel_diff(fg, fo) < 2e-3
+
+
 def test_kernel_times_and_stats(scenes):
+    """Instrumentation is a run-time opt-in (RptRenderParams.flags): off -> no per-kernel times, no BVH work counters;
+    on -> both, and the film is the same."""
     st, cs, _ = scenes("cornell", 96, 54, 8)
-    cs.render_pt(st.params(seed=1))
+    f0, c0 = cs.render_pt(st.params(seed=1))
+    assert cs.kernel_times() == [] or all(k["ms"] == 0.0 for k in cs.kernel_times())
+    assert c0.walk_nodes == 0 and c0.walk_tris == 0 and c0.kernel_launches > 0 and c0.device_ms > 0
+    f1, c1 = cs.render_pt(st.params(seed=1, flags=3))
     names = [k["name"] for k in cs.kernel_times()]
     assert "k_trace" in names and "k_shadow" in names and "k_film" in names
+    assert c1.walk_tris + c1.walk_nodes > 0 and c1.segments == c0.segments
+    assert np.allclose(f0, f1, rtol=1e-6, atol=1e-9)
     s = cs.stats()
     assert s["triangles"] == 30 and s["instances"] == 4

@@ -12,7 +12,7 @@ for so in sys.argv[2:]:
     sc = p.ffi.Scene(lib, flat, 0)
     best = None
     for i in range(3):
-        ptr, cnt = sc.render_pt_device(st.params(seed=i, spp_total=0))
+        ptr, cnt = sc.render_pt_device(st.params(seed=i, spp_total=0, flags=1))
         kt = {k["name"]: k["ms"] for k in sc.kernel_times()}
         if best is None or cnt.device_ms < best[0]:
             best = (cnt.device_ms, kt, cnt.segments)
