@@ -60,13 +60,16 @@ def save_world(path: str, world: W.World, settings: dict, lambda_lo: float, lamb
                  sharpness=m.sharpness, sidedness=m.sidedness, metallic=bool(m.metallic))
             for m in world.materials
         ],
-        "textures": [dict(channels=t.channels, curves=list(t.curves)) for t in world.textures],
+        "textures": [dict(channels=t.channels, curves=list(t.curves), recipe=t.recipe) for t in world.textures],
         "texstacks": world.texstacks,
         "env": dict(kind=world.environment.kind, strength=world.environment.strength, curve=world.environment.curve,
                     angular_diameter=world.environment.angular_diameter, sun_direction=list(world.environment.sun_direction),
                     texstack=world.environment.texstack, rotation=_t3(world.environment.rotation),
                     imap_marginal_integral=world.environment.imap_marginal_integral,
-                    has_imap=world.environment.imap_row_pdf is not None),
+                    has_imap=world.environment.imap_row_pdf is not None,
+                    # ImportanceMap::Unbaked (importance_map.rs:32-46): resolution only; the tables are baked where the blob is
+                    # loaded (on the device by CudaRenderer / tests, naive.rs:469-487). Only the default luminance curve (y_bar).
+                    imap_request=None if world.environment.imap_request is None else list(world.environment.imap_request[:2])),
         "env_sampling_probability": world.env_sampling_probability,
         "cameras": [
             dict(name=c.name, origin=c.origin.tolist(), u=c.u.tolist(), v=c.v.tolist(), w=c.w.tolist(), lower_left=c.lower_left.tolist(),
@@ -85,7 +88,8 @@ def save_world(path: str, world: W.World, settings: dict, lambda_lo: float, lamb
         if m.normals is not None:
             arrays[f"mesh{i}_n"] = m.normals
     for i, t in enumerate(world.textures):
-        arrays[f"tex{i}"] = t.texels
+        if t.recipe is None:  # (a synthetic map travels as its recipe: a 4096x2048 environment is 134 MB of texels)
+            arrays[f"tex{i}"] = t.texels
     e = world.environment
     if e.imap_row_pdf is not None:
         arrays.update(imap_row_pdf=e.imap_row_pdf, imap_row_cdf=e.imap_row_cdf, imap_m_pdf=e.imap_marginal_pdf, imap_m_cdf=e.imap_marginal_cdf)
@@ -109,7 +113,13 @@ def load_world(path: str) -> Tuple[W.World, dict, Tuple[float, float, int]]:
     for d in meta["materials"]:
         world.materials.append(W.Material(**d))
     for i, d in enumerate(meta["textures"]):
-        world.textures.append(W.Texture(d["channels"], z[f"tex{i}"], tuple(d["curves"])))
+        recipe = d.get("recipe")
+        if recipe is not None:
+            from .synth import texels_from_recipe
+
+            world.textures.append(W.Texture(d["channels"], texels_from_recipe(recipe), tuple(d["curves"]), recipe))
+        else:
+            world.textures.append(W.Texture(d["channels"], z[f"tex{i}"], tuple(d["curves"])))
     world.texstacks = meta["texstacks"]
     e = meta["env"]
     env = W.Environment(kind=e["kind"], strength=e["strength"], curve=e["curve"], angular_diameter=e["angular_diameter"],
@@ -118,6 +128,8 @@ def load_world(path: str) -> Tuple[W.World, dict, Tuple[float, float, int]]:
     if e["has_imap"]:
         env.imap_row_pdf, env.imap_row_cdf = z["imap_row_pdf"], z["imap_row_cdf"]
         env.imap_marginal_pdf, env.imap_marginal_cdf = z["imap_m_pdf"], z["imap_m_cdf"]
+    if e.get("imap_request") is not None and not e["has_imap"]:
+        env.imap_request = (int(e["imap_request"][0]), int(e["imap_request"][1]), C.y_bar_curve())
     world.environment = env
     world.env_sampling_probability = meta["env_sampling_probability"]
     for d in meta["cameras"]:

@@ -1234,15 +1234,16 @@ __global__ void __launch_bounds__(256) k_probe_bw(const float4 *__restrict__ src
     for (uint32_t r = 0; r < reps; ++r)
       for (uint64_t i = tid; i < half; i += stride) dst[half + i] = src[i];
   } else {
+    // every thread issues `reps` independent gathers whatever the footprint, so small (cache-resident) footprints are
+    // measured at the same parallelism as large ones
     const uint64_t nrec = n16 / 4;
     uint64_t x = tid * 0x9E3779B97F4A7C15ull + 12345u;
-    for (uint32_t r = 0; r < reps; ++r)
-      for (uint64_t i = tid; i < nrec; i += stride) {
-        x = x * 6364136223846793005ull + 1442695040888963407ull;
-        const float4 *p = src + 4 * ((x >> 20) % nrec);
-        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
-        acc += a.x + b.y + c.z + d.w;
-      }
+    for (uint32_t r = 0; r < reps; ++r) {
+      x = x * 6364136223846793005ull + 1442695040888963407ull;
+      const float4 *p = src + 4 * ((x >> 20) % nrec);
+      float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+      acc += a.x + b.y + c.z + d.w;
+    }
   }
   if (acc == 123.456f) *sink = acc;  // keeps the loads alive
 }
@@ -2518,7 +2519,7 @@ int rpt_probe_bandwidth(int device, uint64_t bytes, uint32_t reps, int mode, dou
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, e0, e1);
-    double moved = mode == 1 ? (double)(n16 / 2) * 32.0 * reps : (mode == 2 ? (double)(n16 / 4) * 64.0 * reps : (double)n16 * 16.0 * reps);
+    double moved = mode == 1 ? (double)(n16 / 2) * 32.0 * reps : (mode == 2 ? (double)sms * 8 * 256 * 64.0 * reps : (double)n16 * 16.0 * reps);
     if (it > 0) best = std::max(best, moved / (ms * 1e-3) / 1e9);
   }
   cudaEventDestroy(e0);

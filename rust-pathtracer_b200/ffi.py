@@ -227,6 +227,7 @@ class FlatScene:
     def __init__(self, world: W.World, lambda_lo: float, lambda_hi: float, num_lambda: int = 1024):
         self.keep: List[object] = []
         self.world = world
+        self.lambda_bounds = (float(lambda_lo), float(lambda_hi))
         k = self.keep
         d = RptSceneDesc()
         d.abi_version = ABI_VERSION

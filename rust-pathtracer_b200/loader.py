@@ -423,13 +423,28 @@ def construct_world(config: Config, scene_file: Optional[str] = None, resolver: 
                 cids = tuple(ct.resolve(r) for r in refs)
                 img = _read_image_rgba8(resolver.path(layer["filename"])).astype(F32) / F32(255.0)
                 tex = W.Texture(4, img, cids)
-            elif t == "HDR":
+            elif t in ("HDR", "EXR"):
+                # parsing/texture.rs:49-120: both decode to an RGBA f32 image; alpha_fill replaces the alpha channel
                 cids = tuple(ct.resolve(r) for r in layer["curves"])
-                rgb = _read_hdr(resolver.path(layer["filename"]))
-                alpha = np.full(rgb.shape[:2] + (1,), F32(layer.get("alpha_fill") or 0.0), dtype=F32)
+                path = resolver.path(layer["filename"])
+                if t == "HDR":
+                    rgb = _read_hdr(path)
+                else:
+                    from .exr import read_exr_rgb  # uncompressed f32 scanline files (what the synthetic fixtures are written as)
+
+                    try:
+                        rgb = read_exr_rgb(path)
+                    except ValueError as e:
+                        raise LoadError(f"{path}: {e} (only uncompressed FLOAT scanline EXR is decoded here)")
+                alpha_fill = float(layer.get("alpha_fill") or 0.0)
+                alpha = np.full(rgb.shape[:2] + (1,), F32(alpha_fill), dtype=F32)
                 tex = W.Texture(4, np.concatenate([rgb, alpha], axis=2), cids)
+                if os.path.exists(path + ".recipe.json"):  # synthetic fixture: remember how to regenerate it (rust-pathtracer_b200/synth.py)
+                    import json
+
+                    tex.recipe = dict(json.load(open(path + ".recipe.json")), alpha_fill=alpha_fill)
             else:
-                raise LoadError(f"texture type {t} unsupported here (EXR needs the `exr` crate)")
+                raise LoadError(f"texture type {t} unsupported")
             if any(c is None for c in tex.curves):
                 raise LoadError("failed to parse curve (texture.rs:190)")
             world.textures.append(tex)

@@ -152,6 +152,7 @@ class Texture:
     channels: int
     texels: np.ndarray  # (h, w, channels) f32
     curves: Tuple[int, int, int, int]
+    recipe: Optional[dict] = None  # synth.py recipe that regenerates `texels` (synthetic environment maps; scene blobs store it instead)
 
 
 @dataclass

@@ -52,14 +52,24 @@ def load_scene(name: str, width: Optional[int] = None, height: Optional[int] = N
     return world, st, flat
 
 
+def _bake_unbaked_importance_map(scene, flat):
+    """ImportanceMap::Unbaked -> baked before the first render (reference src/renderer/naive.rs:469-487), through the scene's own
+    library: rpt_scene_bake_importance_map on the device, rpto_scene_bake_importance_map in the oracle."""
+    env = flat.world.environment
+    if env.kind == 2 and env.imap_row_pdf is None and env.imap_request is not None:
+        rows, cols, lum = env.imap_request
+        pkg().importance_map.bake_importance_map_on_device(scene, flat.world, rows, cols, lum, flat.lambda_bounds, download=False)
+    return scene
+
+
 def cuda_scene(flat, device: int = 0):
     p = pkg()
-    return p.ffi.Scene(p.ffi.load_library(), flat, device)
+    return _bake_unbaked_importance_map(p.ffi.Scene(p.ffi.load_library(), flat, device), flat)
 
 
 def oracle_scene(flat):
     p = pkg()
-    return p.ffi.Scene(oracle_lib(), flat, 0, "rpto")
+    return _bake_unbaked_importance_map(p.ffi.Scene(oracle_lib(), flat, 0, "rpto"), flat)
 
 
 def oracle_samples(scene, params) -> np.ndarray:

@@ -21,6 +21,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import __graft_entry__ as g  # noqa: E402
 
 pkg = g.load_package()
@@ -293,6 +294,23 @@ look_from = [0.0, -0.5, 1.0]
 look_at = [1.0, 0.2, 0.2]
 fov = [360.0, 160.0]
 """)
+    # C3 as BASELINE.json states it ("dispersive Cauchy dielectric and spectral metals"): the shipped gem scene
+    # (data/scenes/cornell_box_diamond_gem.toml, verbatim) plus the five tabulated-eta/kappa metal spheres of
+    # data/scenes/cornell_box_metals_and_dielectrics.toml:89-119 (gold, iron, copper, platinum, lead), the quad at that scene's
+    # own positions and the gold sphere moved from the centre (where the gem sits) to behind it.
+    ref_gem = open("/root/reference/data/scenes/cornell_box_diamond_gem.toml").read()
+    head, cams = ref_gem.split("[[cameras]]", 1)
+    spheres = "".join(f"""
+[[instances]]
+material_name = "{m}"
+[instances.aggregate]
+type = "Sphere"
+radius = 0.2
+origin = [{x}, {y}, -0.79]
+""" for m, x, y in (("ggx_gold", 0.55, 0.0), ("ggx_iron", 0.51, 0.51), ("ggx_copper", 0.51, -0.51), ("ggx_platinum", -0.51, 0.71), ("ggx_lead", -0.51, -0.71)))
+    with open(os.path.join(GEN, "gem_metals.toml"), "w") as f:
+        f.write(head + spheres + "\n[[cameras]]" + cams)
+
     # instanced monkeys (C5): 48 x 50 grid (minus 12) = 2388 instances, Philox-free numpy RNG seed 5
     rng = np.random.default_rng(5)
     mats = ["lambertian_white", "ggx_gold", "ggx_copper", "ggx_glass"]
@@ -362,14 +380,26 @@ vfov = 50.0
         f.write("".join(lines))
 
 
-def bake(name, cfg, scene_file=None, num_lambda=1024):
-    world = loader.construct_world(cfg, scene_file)
+def bake(name, cfg, scene_file=None, num_lambda=1024, bake_importance_map=True):
+    world = loader.construct_world(cfg, scene_file, bake_importance_map=bake_importance_map)
     rs = cfg.render_settings[0]
     st = PTSettings.from_render_settings(rs, cfg.camera_names_to_index[rs.camera_id])
     path = os.path.join(OUT, name + ".npz")
     blob.save_world(path, world, st.to_dict(), st.wavelength_bounds[0], st.wavelength_bounds[1], num_lambda)
     tris = sum(len(world.meshes[i.mesh].indices) for i in world.instances if i.mesh >= 0)
     print(f"{name:28s} {os.path.getsize(path) / 1024:9.1f} KiB  instances={len(world.instances)} tris(instanced)={tris} lights={len(world.lights)}")
+
+
+def bake_hdri_small():
+    import make_fixtures
+
+    path = os.path.join(ROOT, "fixtures", "data", "hdri", "machine_shop_03_4k.hdr")
+    make_fixtures.write_synthetic_map(path, 1024, 41)
+    os.remove(path + ".recipe.json")  # texels stored in the blob
+    try:
+        bake("hdri", from_reference_config("data/config_test_lighting_hdri.toml", width=3840, height=2160))
+    finally:
+        make_fixtures.write_synthetic_map(path, 4096, 41)
 
 
 def main():
@@ -380,15 +410,25 @@ def main():
     write_generated_scenes()
     # the synthetic HDRs must exist before the HDRI scenes are parsed (small ones for the blobs)
     import subprocess
-    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_fixtures.py"), "--hdri", "--hdri-width", "1024"])
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_fixtures.py"), "--hdri"])
 
     jobs = {
         # BASELINE configs[0]: Cornell, PT, 1080p @ 16 spp (the config file says 1080x1080 @ 128)
         "cornell": lambda: bake("cornell", from_reference_config("data/config_test_cornell_box.toml", width=1920, height=1080, min_samples=16)),
         "furnace": lambda: bake("furnace", from_reference_config("data/config_test_whitefurnace.toml")),
         "furnace_exact": lambda: bake("furnace_exact", make_config("data/scenes/furnace_exact.toml", 256, 256, 64, 1, 8, 4)),
-        "gem": lambda: bake("gem", make_config("data/scenes/cornell_box_diamond_gem.toml", 1920, 1080, 1024, 4, 16, 2)),
-        "hdri": lambda: bake("hdri", from_reference_config("data/config_test_lighting_hdri.toml", width=3840, height=2160)),
+        "gem": lambda: bake("gem", make_config("data/scenes/gem_metals.toml", 1920, 1080, 1024, 4, 16, 2)),
+        # BASELINE configs[3]: data/config_test_lighting_hdri.toml at 4K. Its own scene file (hdri_test.toml: one Lambertian
+        # sphere) is "hdri"; "hdri2" is data/scenes/hdri_test_2.toml (GGX gold / copper / dispersive glass spheres, p_env 0.5,
+        # 1000 x 1000 importance map) under the same render settings - the scene the config's description names. Both sample a
+        # synthetic 4096 x 2048 map (134 MB of RGBA f32 texels, stored in the blob as a recipe) and leave the importance map
+        # Unbaked: it is baked on the device when the scene is created (naive.rs:469-487).
+        # ("hdri" is the round-1 blob: the same scene file over a 1024 x 512 map with the importance map baked on the host
+        # and stored; the parity / golden tests of the importance-map code keep using it)
+        "hdri": bake_hdri_small,
+        "hdri_4k": lambda: bake("hdri_4k", from_reference_config("data/config_test_lighting_hdri.toml", width=3840, height=2160), bake_importance_map=False),
+        "hdri2": lambda: bake("hdri2", from_reference_config("data/config_test_lighting_hdri.toml", width=3840, height=2160),
+                              scene_file="data/scenes/hdri_test_2.toml", bake_importance_map=False),
         "instanced_monkeys": lambda: bake("instanced_monkeys", make_config("data/scenes/instanced_monkeys.toml", 3840, 2160, 16, 2, 6, 2)),
         # in-tree scenes covering the remaining materials / lights / environments
         "test_nee_sphere": lambda: bake("test_nee_sphere", make_config("data/scenes/test_nee_sphere.toml", 512, 512, 32, 2, 8, 2)),

@@ -12,6 +12,6 @@ out = {"how": "rpt_probe_bandwidth (csrc/rpt_kernels.cu k_probe_bw), best of 4 l
 out["l2_stream_read_gbps"] = {f"{mb}MB": p.ffi.probe_bandwidth(lib, 0, mb * MB, max(1, 2048 // mb), 0) for mb in (8, 16, 32, 64, 96)}
 out["hbm_stream_read_gbps"] = {"4096MB": p.ffi.probe_bandwidth(lib, 0, 4096 * MB, 1, 0)}
 out["hbm_copy_gbps"] = {"4096MB": p.ffi.probe_bandwidth(lib, 0, 4096 * MB, 1, 1)}
-out["gather64_gbps"] = {f"{mb}MB": p.ffi.probe_bandwidth(lib, 0, int(mb * MB), max(1, int(512 // mb)), 2) for mb in (0.75, 8, 32, 64, 1024)}
+out["gather64_gbps"] = {f"{mb}MB": p.ffi.probe_bandwidth(lib, 0, int(mb * MB), 256, 2) for mb in (0.125, 0.75, 8, 32, 64, 1024)}  # 256 gathers per thread
 out["l2_peak_gbps"] = max(out["l2_stream_read_gbps"].values())
 print(json.dumps(out, indent=1))

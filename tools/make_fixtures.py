@@ -13,9 +13,18 @@
 Deterministic; safe to re-run.
 """
 import argparse
+import json
 import os
+import sys
 
 import numpy as np
+
+ROOT_ = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT_)
+import __graft_entry__ as _g  # noqa: E402
+
+_g.load_package()
+from rust_pathtracer_b200 import exr, synth  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FIX = os.path.join(ROOT, "fixtures", "data")
@@ -66,40 +75,10 @@ def write_cornell():
             f.write(f"newmtl {mat}\nKd 0.8 0.8 0.8\n\n")
 
 
-def synth_hdr(width: int, height: int, seed: int) -> np.ndarray:
-    """Vertical sky gradient + sun disc + three soft windows + low-amplitude value noise (float32 RGB)."""
-    rng = np.random.default_rng(seed)
-    v = (np.arange(height, dtype=np.float32) + 0.5) / height
-    u = (np.arange(width, dtype=np.float32) + 0.5) / width
-    sky = (2.0 - 1.8 * v)[:, None] * np.ones((1, width), dtype=np.float32)
-    img = np.stack([sky * 0.8, sky * 0.9, sky * 1.1], axis=2).astype(np.float32)
-    # sun: radius 1.5 degrees at (u, v) = (0.7, 0.25)
-    theta = (u[None, :] - 0.5) * 2 * np.pi
-    phi = v[:, None] * np.pi
-    d = np.stack([np.sin(phi) * np.cos(theta), np.sin(phi) * np.sin(theta), np.cos(phi) * np.ones_like(theta)], axis=2)
-    st, sp = (0.7 - 0.5) * 2 * np.pi, 0.25 * np.pi
-    sd = np.array([np.sin(sp) * np.cos(st), np.sin(sp) * np.sin(st), np.cos(sp)], dtype=np.float32)
-    cosang = (d @ sd).astype(np.float32)
-    img[cosang > np.cos(np.deg2rad(1.5))] = np.array([5e4, 4.6e4, 4e4], dtype=np.float32)
-    for (u0, u1, v0, v1, val) in ((0.05, 0.15, 0.40, 0.55, 200.0), (0.30, 0.36, 0.45, 0.60, 50.0), (0.85, 0.95, 0.35, 0.50, 120.0)):
-        mu = np.clip(np.minimum(u - u0, u1 - u) / 0.01, 0, 1)
-        mv = np.clip(np.minimum(v - v0, v1 - v) / 0.01, 0, 1)
-        img += (mv[:, None] * mu[None, :])[..., None] * val
-    coarse = rng.random((height // 32 + 1, width // 32 + 1)).astype(np.float32)
-    noise = np.kron(coarse, np.ones((32, 32), dtype=np.float32))[:height, :width]
-    img *= (0.9 + 0.2 * noise)[..., None]
-    return img.astype(np.float32)
-
-
 def write_hdr(path: str, rgb: np.ndarray) -> None:
     """Uncompressed (flat) Radiance RGBE."""
     h, w, _ = rgb.shape
-    m = np.max(rgb, axis=2)
-    mant, exp = np.frexp(m)
-    scale = np.where(m > 1e-32, 256.0 / np.ldexp(1.0, exp), 0.0).astype(np.float64)
-    rgbe = np.zeros((h, w, 4), dtype=np.uint8)
-    rgbe[..., :3] = np.clip(rgb * scale[..., None], 0, 255).astype(np.uint8)
-    rgbe[..., 3] = np.where(m > 1e-32, exp + 128, 0).astype(np.uint8)
+    rgbe = synth.rgbe_encode(rgb)
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "wb") as f:
         f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n")
@@ -107,16 +86,32 @@ def write_hdr(path: str, rgb: np.ndarray) -> None:
         f.write(rgbe.tobytes())
 
 
+def write_synthetic_map(path: str, width: int, seed: int) -> None:
+    """Writes the synthetic environment map as .hdr (RGBE) or .exr (f32) plus the `<file>.recipe.json` sidecar that lets
+    the loader / scene blobs regenerate it (rust-pathtracer_b200/synth.py)."""
+    rgb = synth.synth_hdr(width, width // 2, seed)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    if path.endswith(".exr"):
+        exr.write_exr_rgb(path, rgb)
+        enc = "f32"
+    else:
+        write_hdr(path, rgb)
+        enc = "rgbe"
+    with open(path + ".recipe.json", "w") as f:
+        json.dump({"kind": "synth_hdr", "width": width, "height": width // 2, "seed": seed, "encoding": enc}, f)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--hdri", action="store_true", help="also write the synthetic HDR environment maps")
-    ap.add_argument("--hdri-width", type=int, default=4096)
+    ap.add_argument("--hdri-width", type=int, default=4096, help="width of the two maps BASELINE config #4 samples (SURVEY Appendix C2: 4096x2048)")
     args = ap.parse_args()
     write_cornell()
     if args.hdri:
         w = args.hdri_width
-        write_hdr(os.path.join(FIX, "hdri", "machine_shop_03_4k.hdr"), synth_hdr(w, w // 2, 41))
-        write_hdr(os.path.join(FIX, "hdri", "kiara_1_dawn_8k.hdr"), synth_hdr(w, w // 2, 42))
+        write_synthetic_map(os.path.join(FIX, "hdri", "machine_shop_03_4k.hdr"), w, 41)                   # hdri_test.toml (config #4's scene file)
+        write_synthetic_map(os.path.join(FIX, "hdri", "kloofendal_43d_clear_puresky_1k.exr"), w, 43)      # hdri_test_2.toml ("low_res_hdri", lib_textures.toml:25-28)
+        write_synthetic_map(os.path.join(FIX, "hdri", "kiara_1_dawn_8k.hdr"), 1024, 42)                   # gem scene: p_env = 0, only ever looked up by escaping rays
     print("fixtures written under", FIX)
 
 

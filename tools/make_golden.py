@@ -40,7 +40,7 @@ film, _ = sc.render_pt(st.params(seed=11))
 np.save(os.path.join(G, "cornell_oracle_16x9.npy"), film)
 # one tiny film per scene blob: pins every oracle code path (materials, lights, environments, instancing, cameras)
 films = {}
-for name in ["cornell", "furnace", "furnace_exact", "gem", "hdri", "test_nee_sphere", "orb_caustic", "sun_test", "rtiow2", "instanced_monkeys", "kitchen_sink"]:
+for name in ["cornell", "furnace", "furnace_exact", "gem", "hdri", "hdri2", "test_nee_sphere", "orb_caustic", "sun_test", "rtiow2", "instanced_monkeys", "kitchen_sink"]:
     world, st, flat = parity.load_scene(name, 16, 12, 4)
     sc = parity.oracle_scene(flat)
     films[name], _ = sc.render_pt(st.params(seed=11))
