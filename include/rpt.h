@@ -319,6 +319,41 @@ typedef struct RptImapBake {
 int rpt_scene_bake_importance_map(RptScene *scene, const RptImapBake *bake, float *row_pdf, float *row_cdf, float *marginal_pdf,
                                   float *marginal_cdf, float *marginal_integral);
 
+/* ---- Multi-GPU: the spp split + film exchange behind the C ABI -----------------------------------------
+ * The reference is one process with one `Renderer::render` call (src/bin/main.rs:59-68,170; src/renderer/mod.rs:107-112),
+ * so a `CudaRenderer { devices: Vec<u32> }` needs the whole multi-GPU job behind ONE call from ONE host thread.
+ * rpt_multi_create uploads a replica of the scene to every listed device (devices[0] is the root) and prepares the film
+ * exchange; rpt_multi_render_pt splits params->spp over the devices (remainder to the low ranks; device i continues the
+ * Philox sample index where device i-1 stopped, so the samples are exactly those of a single-device render of params->spp),
+ * renders with one host worker thread per device, sums the un-normalised XYZ films onto the root, normalises by
+ * params->spp_total and downloads the film (film_xyzw may be NULL: the result stays on the root device,
+ * rpt_multi_scene(multi, 0) + rpt_output_film can tonemap it there).
+ * Exchange: RPT_MULTI_PEER = one fused reduce-scatter + normalise + gather kernel per device over NVLink peer mappings
+ * (default when the devices can map each other); RPT_MULTI_NCCL = ncclReduce(sum) to the root + normalisation kernel
+ * (NCCL is dlopen'ed on first use: libnccl.so.2, or $RPT_NCCL_LIB; forced with RPT_MULTI_REDUCE=nccl). */
+enum RptMultiMethod { RPT_MULTI_PEER = 0, RPT_MULTI_NCCL = 1 };
+typedef struct RptMulti RptMulti; /* opaque */
+typedef struct RptMultiTimes {
+  uint32_t method;               /* RptMultiMethod actually used */
+  uint32_t devices;
+  double render_device_ms_max;   /* slowest device's render, CUDA events on its stream */
+  double exchange_device_ms;     /* film exchange + normalisation, CUDA events, max over devices */
+  double render_wall_ms;         /* host wall clock of the three phases of the call */
+  double exchange_wall_ms;
+  double download_wall_ms;
+} RptMultiTimes;
+int rpt_multi_create(const RptSceneDesc *desc, const int *devices, int n, RptMulti **out);
+int rpt_multi_destroy(RptMulti *multi);
+/* The replica on devices[index] (for rpt_output_film, rpt_scene_stats, rpt_last_kernel_times ...). Owned by `multi`. */
+int rpt_multi_scene(RptMulti *multi, int index, RptScene **scene);
+/* rpt_scene_bake_importance_map on every replica (tables stay on the devices). */
+int rpt_multi_bake_importance_map(RptMulti *multi, const RptImapBake *bake);
+/* counters: sums over the devices; counters->device_ms = slowest device's render + exchange. times may be NULL. */
+int rpt_multi_render_pt(RptMulti *multi, const RptRenderParams *params, float *film_xyzw, RptCounters *counters, RptMultiTimes *times);
+/* One-shot form: create, render, destroy. */
+int rpt_render_pt_multi(const RptSceneDesc *desc, const int *devices, int n, const RptRenderParams *params, float *film_xyzw,
+                        RptCounters *counters);
+
 /* Bandwidth probe: the measured denominators of the roofline fractions (north_star: "achieved HBM/L2 GB/s ... against B200
  * peak"; SURVEY §8d asks for an L2-resident streaming-kernel peak measured on the box). Allocates `bytes`, runs the pattern
  * `reps` times per launch, returns the best of 4 timed launches in GB/s. mode 0: streaming 128-bit reads (L2 bandwidth when

@@ -1379,7 +1379,7 @@ struct RptScene {
   size_t stack_smem = 0;
   uint32_t env_stack_count = 0;  // textures in the environment's stack (HDR)
   bool has_ggx = true;     // any material of the GGX class (else its shade kernel is never launched)
-  int trav_mode = TRAV_BVH;  // TRAV_SMALL for scenes of <= RPT_SMALL_MAX leaves without a BLAS (RPT_NO_SMALL=1 keeps the BVH);
+  int trav_mode = TRAV_BVH;  // TRAV_SMALL (RPT_SMALL=1) for scenes of <= RPT_SMALL_MAX leaves without a BLAS;
                              // TRAV_BVH_TMA: k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
   size_t counts_cap = 0;     // bounces the per-bounce counter block has room for
   // timing of the last render
@@ -1818,6 +1818,9 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
 
 }  // namespace
 
+// rpt_multi.cu reports its errors through the same thread-local string (internal: not part of include/rpt.h)
+extern "C" __attribute__((visibility("hidden"))) void rpt_set_last_error(const char *msg) { g_error = msg ? msg : ""; }
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -2052,8 +2055,12 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   std::vector<float> small_boxes;
   uint32_t small_ntri = 0;
   {
-    const char *e = std::getenv("RPT_NO_SMALL");
-    const bool allow = !(e && e[0] == '1');
+    // Opt-in (RPT_SMALL=1): measured on the B200 (profiles/r02_small_vs_bvh.md) the lockstep leaf walk does run 32 of 32
+    // lanes, but it executes 74-85 warp instructions per Cornell ray against the BVH walk's 35 (coherent first bounce) to 85
+    // (incoherent bounces), and any-hit NEE rays lose the BVH's early exit: the frame is 11 % slower. It stays selectable
+    // and covered by the parity suite (test_small_scene_mode_equals_bvh).
+    const char *e = std::getenv("RPT_SMALL");
+    const bool allow = e && e[0] == '1';
     if (allow && needed_blas_depth == 0 && leaves.size() <= RPT_SMALL_MAX) {
       for (int pass = 0; pass < 2; ++pass)  // triangles first, then whole instances
         for (size_t l = 0; l < leaves.size(); ++l) {

@@ -142,11 +142,24 @@ class RptSceneStats(ct.Structure):
     ]
 
 
+class RptMultiTimes(ct.Structure):
+    _fields_ = [
+        ("method", c_u32), ("devices", c_u32), ("render_device_ms_max", ct.c_double), ("exchange_device_ms", ct.c_double),
+        ("render_wall_ms", ct.c_double), ("exchange_wall_ms", ct.c_double), ("download_wall_ms", ct.c_double),
+    ]
+
+    def as_dict(self) -> dict:
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["method"] = {0: "peer", 1: "nccl"}[int(self.method)]
+        return d
+
+
 # Every symbol include/rpt.h declares (tests/test_abi.py checks the .so exports all of them).
 RPT_SYMBOLS = [
     "rpt_last_error", "rpt_abi_version", "rpt_device_count", "rpt_scene_create", "rpt_scene_destroy",
     "rpt_render_pt", "rpt_render_pt_device", "rpt_trace_primary", "rpt_trace_rays", "rpt_film_scale",
     "rpt_last_kernel_times", "rpt_scene_stats", "rpt_output_film", "rpt_scene_bake_importance_map", "rpt_probe_bandwidth",
+    "rpt_multi_create", "rpt_multi_destroy", "rpt_multi_scene", "rpt_multi_bake_importance_map", "rpt_multi_render_pt", "rpt_render_pt_multi",
 ]
 
 
@@ -201,6 +214,18 @@ def load_library(path: Optional[str] = None) -> ct.CDLL:
     lib.rpt_scene_stats.restype = ct.c_int
     lib.rpt_output_film.argtypes = [ct.c_void_p, ct.c_void_p, c_u32, c_u32, ct.POINTER(RptOutputSettings), ct.c_void_p, ct.c_void_p, ct.c_void_p]
     lib.rpt_output_film.restype = ct.c_int
+    lib.rpt_multi_create.argtypes = [ct.POINTER(RptSceneDesc), ct.POINTER(ct.c_int), ct.c_int, ct.POINTER(ct.c_void_p)]
+    lib.rpt_multi_create.restype = ct.c_int
+    lib.rpt_multi_destroy.argtypes = [ct.c_void_p]
+    lib.rpt_multi_destroy.restype = ct.c_int
+    lib.rpt_multi_scene.argtypes = [ct.c_void_p, ct.c_int, ct.POINTER(ct.c_void_p)]
+    lib.rpt_multi_scene.restype = ct.c_int
+    lib.rpt_multi_bake_importance_map.argtypes = [ct.c_void_p, ct.POINTER(RptImapBake)]
+    lib.rpt_multi_bake_importance_map.restype = ct.c_int
+    lib.rpt_multi_render_pt.argtypes = [ct.c_void_p, ct.POINTER(RptRenderParams), ct.c_void_p, ct.POINTER(RptCounters), ct.POINTER(RptMultiTimes)]
+    lib.rpt_multi_render_pt.restype = ct.c_int
+    lib.rpt_render_pt_multi.argtypes = [ct.POINTER(RptSceneDesc), ct.POINTER(ct.c_int), ct.c_int, ct.POINTER(RptRenderParams), ct.c_void_p, ct.POINTER(RptCounters)]
+    lib.rpt_render_pt_multi.restype = ct.c_int
     lib.rpt_probe_bandwidth.argtypes = [ct.c_int, c_u64, c_u32, ct.c_int, ct.POINTER(ct.c_double)]
     lib.rpt_probe_bandwidth.restype = ct.c_int
     if lib.rpt_abi_version() != ABI_VERSION:
@@ -472,6 +497,54 @@ class Scene:
     def close(self) -> None:
         if self.handle:
             self._fn("scene_destroy")(self.handle)
+            self.handle = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiScene:
+    """RAII wrapper over RptMulti*: one scene replica per device, spp split + film exchange inside the library
+    (include/rpt.h rpt_multi_*). This is what `CudaRenderer { devices }` of the Rust shim drives from one host thread."""
+
+    def __init__(self, lib: ct.CDLL, flat: FlatScene, devices):
+        self.lib, self.flat, self.devices = lib, flat, list(devices)
+        self.handle = ct.c_void_p()
+        arr = (ct.c_int * len(self.devices))(*self.devices)
+        if lib.rpt_multi_create(ct.byref(flat.desc), arr, len(self.devices), ct.byref(self.handle)) != 0:
+            raise RptError(lib.rpt_last_error().decode("utf-8", "replace"))
+        self.times = RptMultiTimes()
+
+    def _err(self) -> str:
+        return self.lib.rpt_last_error().decode("utf-8", "replace")
+
+    def bake_importance_map(self, rows: int, cols: int, luminance: np.ndarray, basis: np.ndarray, wavelength_bounds) -> None:
+        luminance = np.ascontiguousarray(luminance, dtype=F32)
+        basis = np.ascontiguousarray(basis, dtype=F32)
+        b = RptImapBake()
+        b.rows, b.cols, b.num_samples = rows, cols, len(luminance)
+        b.lambda_lo, b.lambda_hi = wavelength_bounds
+        b.luminance, b.basis = luminance.ctypes.data_as(PF), basis.ctypes.data_as(PF)
+        if self.lib.rpt_multi_bake_importance_map(self.handle, ct.byref(b)) != 0:
+            raise RptError(self._err())
+
+    def render_pt(self, params: RptRenderParams, film_ptr: Optional[int] = None):
+        """-> (film (H, W, 4) f32 mean XYZ or None when film_ptr is given, summed counters). params.spp = TOTAL samples."""
+        film = None
+        if film_ptr is None:
+            film = np.zeros((params.height, params.width, 4), dtype=F32)
+            film_ptr = film.ctypes.data
+        counters = RptCounters()
+        if self.lib.rpt_multi_render_pt(self.handle, ct.byref(params), ct.c_void_p(film_ptr), ct.byref(counters), ct.byref(self.times)) != 0:
+            raise RptError(self._err())
+        return film, counters
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.rpt_multi_destroy(self.handle)
             self.handle = ct.c_void_p()
 
     def __del__(self):

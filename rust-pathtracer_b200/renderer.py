@@ -132,6 +132,20 @@ class CudaRenderer:
             bake_importance_map_on_device(scene, world, rows, cols, lum, wavelength_bounds, download=False)
         return scene
 
+    def make_multi_scene(self, world: W.World, wavelength_bounds: Tuple[float, float], devices) -> "ffi.MultiScene":
+        """`RendererType::Cuda { devices }` of the shim: one replica per device + the in-library spp split and film exchange
+        (rpt_multi_*); the importance map of an Unbaked HDR environment is baked on every device."""
+        flat = ffi.FlatScene(world, wavelength_bounds[0], wavelength_bounds[1], self.num_lambda)
+        ms = ffi.MultiScene(self.lib, flat, devices)
+        env = world.environment
+        if env.kind == 2 and env.imap_row_pdf is None and env.imap_request is not None:
+            from .importance_map import bake_curve_tables
+
+            rows, cols, lum = env.imap_request
+            lum_t, basis_t = bake_curve_tables(world, lum, wavelength_bounds)
+            ms.bake_importance_map(rows, cols, lum_t, basis_t, wavelength_bounds)
+        return ms
+
     def render_sampled(self, scene: ffi.Scene, st: PTSettings, spp: Optional[int] = None, spp_offset: int = 0,
                        spp_total: Optional[int] = None):
         """-> (film (H, W, 4) float32 mean XYZ, counters). One C-ABI call; host film out."""

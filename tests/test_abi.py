@@ -43,7 +43,7 @@ def test_struct_sizes_match_the_c_layout(pkg):
     import subprocess
     import tempfile
 
-    src = '#include <stdio.h>\n#include "rpt.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(RptInstance), sizeof(RptMesh), sizeof(RptMaterial), sizeof(RptTexture), sizeof(RptEnvironment), sizeof(RptCamera), sizeof(RptSceneDesc), sizeof(RptRenderParams), sizeof(RptCounters), sizeof(RptSceneStats), sizeof(RptOutputSettings), sizeof(RptImapBake), sizeof(RptKernelTime));return 0;}\n'
+    src = '#include <stdio.h>\n#include "rpt.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(RptInstance), sizeof(RptMesh), sizeof(RptMaterial), sizeof(RptTexture), sizeof(RptEnvironment), sizeof(RptCamera), sizeof(RptSceneDesc), sizeof(RptRenderParams), sizeof(RptCounters), sizeof(RptSceneStats), sizeof(RptOutputSettings), sizeof(RptImapBake), sizeof(RptKernelTime), sizeof(RptMultiTimes));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
@@ -52,7 +52,7 @@ def test_struct_sizes_match_the_c_layout(pkg):
         sizes = list(map(int, subprocess.check_output([exe]).split()))
     f = pkg.ffi
     mirrors = [f.RptInstance, f.RptMesh, f.RptMaterial, f.RptTexture, f.RptEnvironment, f.RptCamera, f.RptSceneDesc, f.RptRenderParams, f.RptCounters, f.RptSceneStats,
-               f.RptOutputSettings, f.RptImapBake, f.RptKernelTime]
+               f.RptOutputSettings, f.RptImapBake, f.RptKernelTime, f.RptMultiTimes]
     assert sizes == [ct.sizeof(m) for m in mirrors]
 
 

@@ -472,17 +472,18 @@ def test_tma_tile_variant(monkeypatch):
 
 @pytest.mark.parametrize("name", ["cornell", "test_nee_sphere", "rtiow2", "orb_caustic", "sun_test", "furnace", "hdri"])
 def test_small_scene_mode_equals_bvh(monkeypatch, name):
-    """Scenes of <= 64 leaves skip the BVH (warp-uniform walk of the leaf list out of shared memory, SmallTrav); RPT_NO_SMALL=1
-    keeps the BVH walk. Both answer the same query, so hit ids, counters and films are identical (energy atomics reorder)."""
+    """RPT_SMALL=1: scenes of <= 64 leaves skip the BVH (warp-uniform walk of the leaf list out of shared memory, SmallTrav).
+    Both modes answer the same query, so hit ids, counters and films are identical (energy atomics reorder). The mode is
+    opt-in: it runs 32 of 32 lanes but more instructions per ray than the BVH walk (profiles/r02_small_vs_bvh.md)."""
     world, st, flat = parity.load_scene(name, 160, 90, 4)
-    small = parity.cuda_scene(flat)
-    monkeypatch.setenv("RPT_NO_SMALL", "1")
     bvh = parity.cuda_scene(flat)
-    monkeypatch.delenv("RPT_NO_SMALL")
+    monkeypatch.setenv("RPT_SMALL", "1")
+    small = parity.cuda_scene(flat)
+    monkeypatch.delenv("RPT_SMALL")
     p = st.params(seed=9, flags=2)
     fs, cs_ = small.render_pt(p)
     fb, cb = bvh.render_pt(p)
-    assert cs_.walk_nodes == 0 and cb.walk_nodes > 0, "the two scenes must really run the two modes"
+    assert cs_.walk_nodes == 0 and (cb.walk_nodes > 0 or len(world.instances) == 1), "the two scenes must really run the two modes"
     for k in ("segments", "bounce_rays", "shadow_rays", "shadow_rays_traced", "env_hits"):
         assert getattr(cs_, k) == getattr(cb, k), (name, k)
     assert np.allclose(fs, fb, rtol=1e-5, atol=1e-9), (name, float(np.abs(fs - fb).max()))
@@ -519,3 +520,68 @@ def test_kernel_times_and_stats(scenes):
     assert np.allclose(f0, f1, rtol=1e-6, atol=1e-9)
     s = cs.stats()
     assert s["triangles"] == 30 and s["instances"] == 4
+
+
+def _device_count(pkg):
+    import ctypes as ct
+
+    n = ct.c_int()
+    assert pkg.ffi.load_library().rpt_device_count(ct.byref(n)) == 0
+    return n.value
+
+
+@pytest.mark.parametrize("method", ["peer", "nccl"])
+def test_multi_device_render_behind_the_c_abi(pkg, monkeypatch, method):
+    """rpt_multi_*: the spp split, one host thread per device and the film exchange live inside the library (the reference is a
+    single process: src/bin/main.rs:59-68,170). N devices x k spp reproduce the samples of one device x N k spp, so the
+    multi-device film equals the single-device film up to the order of the f32 sums (test_spp_split_equals_whole through
+    the C ABI). Runs on every device count available: with one GPU it covers the n = 1 path, with >= 2 both exchanges
+    (fused NVLink peer kernel; NCCL reduce)."""
+    ndev = _device_count(pkg)
+    devices = list(range(min(ndev, 8)))
+    if method == "nccl":
+        if ndev < 2:
+            pytest.skip("the NCCL exchange needs >= 2 devices")
+        monkeypatch.setenv("RPT_MULTI_REDUCE", "nccl")
+    world, st, flat = parity.load_scene("cornell", 160, 90, 12)
+    single = parity.cuda_scene(flat, 0)
+    f1, c1 = single.render_pt(st.params(seed=77))
+    single.close()
+    ms = pkg.ffi.MultiScene(pkg.ffi.load_library(), flat, devices)
+    fm, cm = ms.render_pt(st.params(seed=77))
+    t = ms.times.as_dict()
+    assert t["devices"] == len(devices) and (len(devices) == 1 or t["method"] == method)
+    assert cm.camera_rays == c1.camera_rays and cm.segments == c1.segments and cm.shadow_rays == c1.shadow_rays
+    assert np.allclose(fm, f1, rtol=2e-5, atol=1e-8), float(np.abs(fm - f1).max())
+    assert (fm[..., 3] == 0).all()
+    # the one-shot form and an uneven split (12 spp over the devices with a different total divisor)
+    p = st.params(seed=78, spp=7, spp_total=7)
+    f7, _ = ms.render_pt(p)
+    import ctypes as ct
+
+    out = np.zeros_like(f7)
+    arr = (ct.c_int * len(devices))(*devices)
+    cnt = pkg.ffi.RptCounters()
+    rc = ms.lib.rpt_render_pt_multi(ct.byref(flat.desc), arr, len(devices), ct.byref(p), out.ctypes.data_as(ct.c_void_p), ct.byref(cnt))
+    assert rc == 0, ms.lib.rpt_last_error()
+    assert np.allclose(out, f7, rtol=2e-5, atol=1e-8) and cnt.camera_rays == 160 * 90 * 7
+    ms.close()
+
+
+def test_multi_device_importance_map_and_errors(pkg):
+    """An Unbaked HDR importance map is baked on every replica (CudaRenderer.make_multi_scene); bad device lists fail loudly."""
+    ndev = _device_count(pkg)
+    devices = list(range(min(ndev, 4)))
+    world, st, flat = parity.load_scene("hdri2", 96, 54, 8)
+    r = pkg.CudaRenderer(device=0, seed=3)
+    ms = r.make_multi_scene(world, st.wavelength_bounds, devices)
+    fm, cm = ms.render_pt(st.params(seed=3))
+    ms.close()
+    sc = parity.cuda_scene(flat, 0)
+    f1, c1 = sc.render_pt(st.params(seed=3))
+    sc.close()
+    assert cm.segments == c1.segments and parity.rel_mse(fm, f1) < 1e-8
+    with pytest.raises(pkg.ffi.RptError):
+        pkg.ffi.MultiScene(pkg.ffi.load_library(), flat, [0, 0])
+    with pytest.raises(pkg.ffi.RptError):
+        pkg.ffi.MultiScene(pkg.ffi.load_library(), flat, [ndev + 3])
