@@ -6,14 +6,21 @@
 One "step" = one pass of the hot path over one batch = rendering the whole 1920x1080 @ 16 spp frame
 (33.2 M camera samples) of scenes/cornell.npz through the CUDA wavefront pipeline, film left on the
 device. `value` = path segments per second (one segment = one walk ray traced + shaded, one iteration of
-reference src/integrator/utils.rs:170), whole job over all N GPUs. Multi-GPU: every rank renders the full
-frame with its own 16 spp (weak scaling, Philox sample offset = rank * 16), then ONE NCCL reduce of the
+reference src/integrator/utils.rs:170), whole job over all N GPUs. Multi-GPU headline: every rank renders the
+full frame with its own 16 spp (WEAK scaling, Philox sample offset = rank * 16), then ONE NCCL reduce of the
 XYZ film to rank 0; the reduce is inside the timed region.
 
-Also on the same JSON line: `e2e` (the same metric through the public API with host buffers: scene upload
-H2D + render + film D2H into pinned memory every step), `roofline` (dominant kernel, algorithmic bytes /
-CUDA-event time vs the measured HBM peak), `cpu_baseline` (the CPU oracle on a bounded sample of the same
-workload, all host threads), `clocks`, `gpu_launches`.
+Also on the same JSON line:
+  e2e            the same metric through the public API with host buffers (scene upload H2D + render + film D2H into
+                 pinned memory, every step)
+  roofline       dominant kernel: algorithmic bytes / CUDA-event time vs the measured HBM peak
+  cpu_baseline   the CPU oracle on a bounded sample of the same workload, all host threads (N = 1 only)
+  strong         STRONG scaling of the same frame: 16 spp and 128 spp TOTAL split over the N GPUs, reduce time separate
+  configs        one record per BASELINE config #2-#5 at its stated size, spp split over the N GPUs + one film reduce:
+                 segments/s, ms, dominant kernel, its HBM (queue records) and L2 (BVH fetch) roofline fractions
+  multi_inprocess  the same weak-scaling frame driven by ONE process through the C ABI's rpt_multi_* (one host thread per
+                 device, fused NVLink peer reduce kernel / NCCL), measured by rank 0 while the other ranks wait
+  clocks, gpu_launches
 
 --impl reference: times the reference's CPU implementation of the path. The reference is Rust nightly with
 two un-vendored git crates and cannot be built in this image, so this arm runs the C++ oracle restatement
@@ -22,6 +29,7 @@ two un-vendored git crates and cannot be built in this image, so this arm runs t
 from __future__ import annotations
 
 import argparse
+import copy
 import gc
 import json
 import os
@@ -40,13 +48,30 @@ UNIT = "segments/s"
 SCENE = "cornell"
 CPU_SAMPLE = (960, 540)  # bounded CPU sample: same scene/spp/bounces, 1/4 of the pixels (~2-3 s per pass on 16 cores)
 
+# BASELINE.json configs #2-#5 at their stated composition and size (configs[0] is the headline above).
+CONFIGS = [
+    {"id": "C2", "scene": "furnace", "what": "data/config_test_whitefurnace.toml, PT, 1024x1024 @ 128 spp"},
+    {"id": "C3", "scene": "gem", "what": "moissanite gem (dispersive Cauchy dielectric) + gold/iron/copper/platinum/lead spheres in the Cornell rects, 1080p @ 1024 spp"},
+    {"id": "C4", "scene": "hdri2", "what": "data/config_test_lighting_hdri.toml settings on hdri_test_2.toml (GGX gold / copper / dispersive glass, importance-sampled "
+                                            "synthetic 4096x2048 HDR, 1000x1000 map baked on the device), 3840x2160 @ 128 spp"},
+    {"id": "C5", "scene": "instanced_monkeys", "what": "2388 instances of data/meshes/monkey.obj (10.0 M triangles), 3840x2160 @ 16 spp"},
+]
+
 
 def load_peaks():
+    """(HBM GB/s, source, L2 GB/s or None, source)."""
+    hbm, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+            hbm, hbm_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    l2, l2_src = None, None
+    p2 = os.path.join(ROOT, "profiles", "r02_peaks.json")
+    if os.path.exists(p2):
+        with open(p2) as f:
+            l2 = float(json.load(f)["l2_peak_gbps"])
+        l2_src = "measured (profiles/r02_peaks.json: rpt_probe_bandwidth, L2-resident streaming 128-bit reads)"
+    return hbm, hbm_src, l2, l2_src
 
 
 class ClockSampler:
@@ -142,6 +167,42 @@ def run_reference(args):
     return 0
 
 
+def kernel_rooflines(c, ktimes, steps, hbm_peak, l2_peak):
+    """Per kernel: algorithmic HBM bytes (the queue records it must move once) and, for the traversal kernels,
+    the BVH bytes it fetches through L1/L2 (nodes * 64 + triangles * 48 + instances * 144), against CUDA-event time.
+    `c` = counters of one instrumented step, ktimes = {name: {ms, launches}} summed over `steps` instrumented steps."""
+    n_vertices = c.bounce_rays - c.camera_rays - c.env_hits  # surface vertices shaded (both classes)
+    # vertex / continuing-path / shadow-record counts are not split per class by the counters: the two shade kernels share the
+    # figure, so per-class fractions are upper bounds on scenes that use both classes
+    shade_bytes = n_vertices * (4 + 64 + 16) + (c.segments - c.camera_rays) * 64 + c.shadow_rays_traced * 36
+    hbm_bytes = {
+        "k_trace": c.segments * (64 + 16 + 4),        # path record in, hit record + class index out
+        "k_shadow": c.shadow_rays_traced * (36 + 4),  # shadow record in, one 4-byte energy RED out
+        "k_shade_surface<diffuse>": shade_bytes,
+        "k_shade_surface<ggx>": shade_bytes,
+        "k_shade_miss": c.env_hits * (4 + 64),
+    }
+    bvh_bytes = {
+        "k_trace": c.walk_nodes * 64 + c.walk_tris * 48 + c.walk_insts * 144,
+        "k_shadow": c.shadow_nodes * 64 + c.shadow_tris * 48 + c.shadow_insts * 144,
+    }
+    out = {}
+    for name, kt in ktimes.items():
+        if kt["launches"] == 0 or kt["ms"] <= 0:
+            continue
+        ms_step = kt["ms"] / steps
+        r = {"ms_per_step": ms_step, "launches_per_step": kt["launches"] / steps}
+        if name in hbm_bytes:
+            r["hbm_gbps"] = hbm_bytes[name] / (ms_step * 1e-3) / 1e9
+            r["hbm_frac"] = r["hbm_gbps"] / hbm_peak
+        if name in bvh_bytes and bvh_bytes[name] > 0:
+            r["bvh_fetch_gbps"] = bvh_bytes[name] / (ms_step * 1e-3) / 1e9
+            if l2_peak:
+                r["l2_frac"] = r["bvh_fetch_gbps"] / l2_peak
+        out[name] = r
+    return out, hbm_bytes, bvh_bytes
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,11 +214,13 @@ def main():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--spp", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config records (BASELINE configs #2-#5)")
+    ap.add_argument("--no-extras", action="store_true", help="skip strong scaling and the in-process multi-GPU leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
 
     import parity
@@ -176,31 +239,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     W = max(args.warmup, 3)
     K = args.steps
-
-    world, st, flat = parity.load_scene(args.scene, args.width, args.height, args.spp)
-    scene = parity.cuda_scene(flat, local_rank)
-    spp = st.min_samples
-    total_spp = spp * world_size  # weak scaling: per-GPU work fixed
-    wh = st.width * st.height
-
-    films = {}
-
-    def step(i: int, flags: int = 0):
-        """One device-resident pass; returns (counters, (e0, e1) torch events around the reduce + normalise)."""
-        if world_size > 1:
-            torch.cuda.current_stream().synchronize()  # the previous step's reduce still reads the film this pass clears
-        ptr, cnt = scene.render_pt_device(st.params(seed=1000 + i, spp=spp, spp_offset=rank * spp, spp_total=0, flags=flags))
-        film = films.get(ptr)
-        if film is None:
-            film = films[ptr] = pkg.renderer.device_tensor(ptr, (st.height, st.width, 4), local_rank)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        if world_size > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            film.mul_(1.0 / total_spp)  # the mean over all samples (tiled.rs:396-398), on the device
-        e1.record()
-        return cnt, (e0, e1)
+    hbm_peak, hbm_src, l2_peak, l2_src = load_peaks()
+    dev = f"cuda:{local_rank}"
 
     def sync():
         torch.cuda.synchronize()
@@ -208,72 +248,112 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allreduce(values, op_name):
+        if dist is None:
+            return [float(x) for x in values]
+        t = torch.tensor([float(x) for x in values], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op_name == "max" else dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    class Job:
+        """One scene on this rank's GPU + the spp split / NCCL film reduce / normalisation around rpt_render_pt_device."""
+
+        def __init__(self, name, width=None, height=None, spp=None):
+            self.world, self.st, self.flat = parity.load_scene(name, width, height, spp)
+            self.scene = parity.cuda_scene(self.flat, local_rank)  # (bakes an Unbaked importance map on the device)
+            self.films = {}
+
+        def step(self, seed, count, offset, total_spp, flags=0):
+            """-> (counters, (e0, e1) torch events around reduce + normalise). Film stays on the device (rank 0 holds the mean)."""
+            if world_size > 1:
+                torch.cuda.current_stream().synchronize()  # the previous step's reduce still reads the film this pass clears
+            st = self.st
+            ptr, cnt = self.scene.render_pt_device(st.params(seed=seed, spp=count, spp_offset=offset, spp_total=0, flags=flags))
+            film = self.films.get(ptr)
+            if film is None:
+                film = self.films[ptr] = pkg.renderer.device_tensor(ptr, (st.height, st.width, 4), local_rank)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if world_size > 1:
+                dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                film.mul_(1.0 / total_spp)  # the mean over all samples (tiled.rs:396-398), on the device
+            e1.record()
+            return cnt, (e0, e1)
+
+        def close(self):
+            self.films.clear()
+            self.scene.close()
+
+    def timed(job, steps, warm, count, offset, total_spp, seed0):
+        """`warm` untimed + `steps` timed steps bracketed by barrier + synchronize; max over ranks. -> dict."""
+        for i in range(warm):
+            job.step(seed0 + i, count, offset, total_spp)
+        sync()
+        gc.collect()
+        gc.disable()
+        t0 = time.perf_counter()
+        dev_ms, segs, launches, pending, cnt = 0.0, 0, 0, [], None
+        for i in range(steps):
+            cnt, ev = job.step(seed0 + warm + i, count, offset, total_spp)
+            dev_ms += cnt.device_ms
+            pending.append(ev)
+            segs += cnt.segments
+            launches += cnt.kernel_launches + (1 if rank == 0 else 0)
+        sync()
+        wall = time.perf_counter() - t0
+        gc.enable()
+        red_ms = sum(e0.elapsed_time(e1) for e0, e1 in pending)
+        dev_ms, wall_ms, red_ms = allreduce([dev_ms + red_ms, wall * 1e3, red_ms], "max")
+        segs_all, launches_all = allreduce([segs, launches], "sum")
+        return {"wall_ms_per_step": wall_ms / steps, "device_ms_per_step": dev_ms / steps, "reduce_ms_per_step": red_ms / steps,
+                "segments_per_step": segs_all / steps, "value": segs_all / (wall_ms * 1e-3), "launches": int(launches_all), "last": cnt}
+
+    def instrumented(job, steps, count, offset, total_spp, seed0):
+        """The same steps with RPT_FLAG_KERNEL_TIMES | RPT_FLAG_BVH_STATS: per-kernel CUDA-event times and BVH work counters."""
+        ktimes, prof_ms, cnt = {}, 0.0, None
+        for i in range(steps):
+            cnt, _ = job.step(seed0 + i, count, offset, total_spp, flags=3)
+            prof_ms += cnt.device_ms
+            for k in job.scene.kernel_times():
+                a = ktimes.setdefault(k["name"], {"ms": 0.0, "launches": 0})
+                a["ms"] += k["ms"]
+                a["launches"] += k["launches"]
+        sync()
+        return ktimes, prof_ms / steps, cnt
+
+    # ------------------------------------------------------------------------------------------ headline (weak scaling)
+    head = Job(args.scene, args.width, args.height, args.spp)
+    st = head.st
+    spp = st.min_samples
+    total_spp = spp * world_size  # weak scaling: per-GPU work fixed
+    wh = st.width * st.height
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()  # started before the warm-up so that samples exist inside the (short) timed region
     for i in range(W):
-        step(i)
+        head.step(i, spp, rank * spp, total_spp)
     sync()
     if sampler:
         sampler.lines.clear()
-    gc.collect()
-    gc.disable()
-    t0 = time.perf_counter()
-    dev_ms, segs, launches, last_cnt = 0.0, 0, 0, None
-    ktimes, pending = {}, []
-    for i in range(K):
-        cnt, ev = step(W + i)
-        dev_ms += cnt.device_ms
-        pending.append(ev)
-        segs += cnt.segments
-        launches += cnt.kernel_launches + (1 if rank == 0 else 0)
-        last_cnt = cnt
-    sync()
-    wall = time.perf_counter() - t0
-    gc.enable()
+    res = timed(head, K, 0, spp, rank * spp, total_spp, 1000)
     clocks = sampler.stop() if sampler else None
-    dev_ms += sum(e0.elapsed_time(e1) for e0, e1 in pending)
-    # Per-kernel CUDA-event times and BVH work counters are a run-time opt-in of the library (RPT_FLAG_KERNEL_TIMES |
-    # RPT_FLAG_BVH_STATS): the K timed steps above run without them; the same K steps are repeated with them for the
-    # per-kernel roofline, and the cost of the instrumentation itself is reported (device_ms_per_step_instrumented).
-    prof_ms = 0.0
-    for i in range(K):
-        cnt, ev = step(W + K + i, flags=3)
-        prof_ms += cnt.device_ms
-        last_cnt = cnt
-        for k in scene.kernel_times():
-            a = ktimes.setdefault(k["name"], {"ms": 0.0, "launches": 0})
-            a["ms"] += k["ms"]
-            a["launches"] += k["launches"]
-    sync()
-
-    # max over ranks / sums over ranks
-    if dist is not None:
-        t = torch.tensor([dev_ms, wall * 1e3], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall = float(t[0]), float(t[1]) / 1e3
-        s = torch.tensor([segs, launches], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        segs_all, launches_all = float(s[0]), int(s[1])
-    else:
-        segs_all, launches_all = float(segs), launches
-    # headline: the bracketed region (barrier + synchronize on both sides), max over ranks; the CUDA-event device
-    # time is reported next to it (device_ms_per_step) and is what the per-kernel roofline uses.
-    value = segs_all / wall
+    value = res["value"]
+    # Per-kernel CUDA-event times and BVH work counters are a run-time opt-in of the library: the K timed steps above run
+    # without them; the same K steps are repeated with them for the per-kernel roofline, and what the instrumentation
+    # itself costs is reported (device_ms_per_step_instrumented vs device_ms_per_step).
+    ktimes, prof_ms, c = instrumented(head, K, spp, rank * spp, total_spp, 3000)
 
     # ---- e2e through the public API with host buffers (scene upload + render + film D2H, every step)
     renderer = pkg.CudaRenderer(device=local_rank)
     pinned = torch.empty((st.height, st.width, 4), dtype=torch.float32).pin_memory()
     e2e_steps = max(2, min(3 * K, 30))  # cheap (24 ms each) and dilutes the host-side stalls a shared box throws in now and then
     h2d = d2h = 0
-
-    import copy
-
     st_all = copy.copy(st)
     st_all.min_samples = total_spp
 
     def e2e_step(i):
-        sc = renderer.make_scene(world, st.wavelength_bounds)  # H2D: the flattened World
+        sc = renderer.make_scene(head.world, st.wavelength_bounds)  # H2D: the flattened World
         if world_size > 1:  # spp split + one NCCL reduce + normalise (CudaRenderer.render_sampled_distributed), film D2H on rank 0
             renderer.seed = 2000 + i
             film, cnt = renderer.render_sampled_distributed(sc, st_all, rank, world_size)
@@ -293,8 +373,7 @@ def main():
     gc.disable()  # as timeit does: a generation-2 collection over torch's object graph is a ~100 ms host stall in one step
     sync()
     te = time.perf_counter()
-    e2e_segs = 0
-    e2e_ms = []
+    e2e_segs, e2e_ms = 0, []
     for i in range(e2e_steps):
         ts = time.perf_counter()
         segs_i, h2d = e2e_step(i)
@@ -304,14 +383,82 @@ def main():
     sync()
     e2e_t = time.perf_counter() - te
     gc.enable()
-    if dist is not None:
-        t = torch.tensor([e2e_t], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_t = float(t[0])
-        s = torch.tensor([e2e_segs], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        e2e_segs = float(s[0])
+    e2e_t = allreduce([e2e_t], "max")[0]
+    e2e_segs = allreduce([e2e_segs], "sum")[0]
     e2e_value = e2e_segs / e2e_t
+
+    # ------------------------------------------------------------------------------------------ strong scaling (same frame)
+    strong = []
+    if not args.no_extras:
+        for total in (16, 128):
+            count, offset = pkg.renderer.split_spp(total, world_size, rank)
+            r = timed(head, 3, 1, count, offset, total, 5000 + total)
+            strong.append({"total_spp": total, "spp_per_gpu": count, "value": r["value"], "unit": UNIT, "ms_per_step": r["wall_ms_per_step"],
+                           "device_ms_per_step": r["device_ms_per_step"], "reduce_ms_per_step": r["reduce_ms_per_step"]})
+    stats_head = head.scene.stats()
+    head.close()
+
+    # ------------------------------------------------------------------------------------------ BASELINE configs #2-#5
+    configs = []
+    if not args.no_configs:
+        for cfg in CONFIGS:
+            job = Job(cfg["scene"])
+            total = job.st.min_samples
+            count, offset = pkg.renderer.split_spp(total, world_size, rank)
+            kt, _, cc = instrumented(job, 1, count, offset, total, 7000)  # doubles as the warm-up
+            r = timed(job, 2, 0, count, offset, total, 7100)
+            roofs_c, _, _ = kernel_rooflines(cc, kt, 1, hbm_peak, l2_peak)
+            dom = max(kt.items(), key=lambda kv: kv[1]["ms"])[0] if kt else None
+            sst = job.scene.stats()
+            configs.append({
+                "id": cfg["id"], "scene": cfg["scene"], "what": cfg["what"], "film": f"{job.st.width}x{job.st.height}", "total_spp": total, "spp_per_gpu": count,
+                "n_gpus": world_size, "scaling": "strong (spp split + one NCCL film reduce)", "value": r["value"], "unit": UNIT,
+                "ms_per_step": r["wall_ms_per_step"], "device_ms_per_step": r["device_ms_per_step"], "reduce_ms_per_step": r["reduce_ms_per_step"],
+                "samples_per_sec": job.st.width * job.st.height * total / (r["wall_ms_per_step"] * 1e-3),
+                "dominant_kernel": dom, "dominant_kernel_roofline": roofs_c.get(dom), "kernel_rooflines_rank0": roofs_c,
+                "scene_bytes": {"nodes": sst["node_bytes"], "triangles": sst["triangle_bytes"], "total": sst["scene_bytes_total"]},
+                "segments_per_sample": r["segments_per_step"] / (job.st.width * job.st.height * total),
+            })
+            job.close()
+
+    # ------------------------------------------------------------------------------------------ in-process multi-GPU (C ABI)
+    multi = None
+    if not args.no_extras:
+        # The other ranks must leave their GPUs idle while rank 0 drives all of them from one process: they wait on the HOST
+        # (a key in the c10d store), not in an NCCL barrier, whose kernel would spin on every waiting GPU.
+        store = dist.distributed_c10d._get_default_store() if dist is not None else None
+        sync()
+        if rank == 0:
+            try:
+                world, st_m, flat = parity.load_scene(args.scene, args.width, args.height, args.spp)
+                multi = {}
+                for method in (["peer", "nccl"] if world_size > 1 else ["peer"]):
+                    if method == "nccl":
+                        os.environ["RPT_MULTI_REDUCE"] = "nccl"
+                    ms = pkg.ffi.MultiScene(pkg.ffi.load_library(), flat, list(range(world_size)))
+                    os.environ.pop("RPT_MULTI_REDUCE", None)
+                    p = st_m.params(seed=9000, spp=spp * world_size, spp_total=spp * world_size)
+                    ms.render_pt(p, film_ptr=pinned.data_ptr())  # warm-up
+                    t0 = time.perf_counter()
+                    segs_m, reps = 0, 3
+                    for i in range(reps):
+                        p.seed = 9001 + i
+                        _, cm = ms.render_pt(p, film_ptr=pinned.data_ptr())
+                        segs_m += cm.segments
+                    dt = time.perf_counter() - t0
+                    multi[method] = dict(ms.times.as_dict(), value_e2e=segs_m / dt, unit=UNIT, ms_per_step_e2e=dt * 1e3 / reps,
+                                         note="rpt_multi_render_pt from ONE host thread: spp split, one worker thread per device, film exchange, "
+                                              "normalisation and the film download into pinned host memory are all inside the call")
+                    ms.close()
+            except Exception as e:  # the headline must not depend on this leg
+                multi = {"error": f"{type(e).__name__}: {e}"}
+            if store is not None:
+                store.set("rpt_multi_done", "1")
+        elif store is not None:
+            import datetime
+
+            store.wait(["rpt_multi_done"], datetime.timedelta(seconds=900))
+        sync()
 
     if rank != 0:
         if dist is not None:
@@ -319,21 +466,7 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel: algorithmic HBM bytes / CUDA-event time (DESIGN.md "Kernels").
-    # Algorithmic HBM bytes = the queue records a kernel must read/write once (the whole scene is a few KB
-    # and stays in L1/L2, so BVH node / triangle fetches are cache traffic: reported separately as bvh_fetch).
-    c = last_cnt
-    stats = scene.stats()
-    n_vertices = c.bounce_rays - c.camera_rays - c.env_hits  # surface vertices shaded
-    hbm_bytes = {
-        "k_trace": c.segments * (64 + 16 + 4),                      # path record in, hit record + class index out
-        "k_shadow": c.shadow_rays_traced * (36 + 4),                # shadow record in, one 4-byte energy RED out
-        "k_shade_surface<diffuse>": n_vertices * (4 + 64 + 16) + (c.segments - c.camera_rays) * 64 + c.shadow_rays_traced * 36,
-    }
-    bvh_bytes = {
-        "k_trace": c.walk_nodes * 64 + c.walk_tris * 48 + c.walk_insts * 144,
-        "k_shadow": c.shadow_nodes * 64 + c.shadow_tris * 48 + c.shadow_insts * 144,
-    }
-    peak, peak_src = load_peaks()
+    roofs, hbm_bytes, bvh_bytes = kernel_rooflines(c, ktimes, K, hbm_peak, l2_peak)
     dominant = max(ktimes.items(), key=lambda kv: kv[1]["ms"])[0] if ktimes else None
     roofline = None
     if dominant in hbm_bytes:
@@ -350,13 +483,16 @@ def main():
                 traffic = tj["kernels"][dominant]["dram_bytes_per_launch"]
                 ncu_share = tj["kernels"][dominant]["share"]
                 traffic_src = "profiles/ncu_traffic.json <- " + tj.get("source", "?") + " (dram__bytes_read.sum + dram__bytes_write.sum per launch, same command)"
-        roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_source": traffic_src, "ncu_time_share": ncu_share, "peak_source": peak_src, "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
-                    "launches_per_step": launches_per_step,
+        roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "traffic_source": traffic_src, "ncu_time_share": ncu_share, "peak_source": hbm_src, "bytes_per_launch": per_launch_bytes,
+                    "ms_per_launch": per_launch_ms, "launches_per_step": launches_per_step,
                     "bvh_fetch_gbps_cache_level": bvh_bytes.get(dominant, 0) / launches_per_step / (per_launch_ms * 1e-3) / 1e9,
+                    "l2_peak": l2_peak, "l2_peak_source": l2_src,
                     "note": "BVH + geometry = %d B, L1-resident: this kernel is bound by instruction issue / L1 latency under divergence, not by HBM; "
-                            "see profiles/ for the ncu issue-slot and branch-efficiency counters" % (stats["node_bytes"] + stats["triangle_bytes"])}
-    kernel_share = {k: v["ms"] / max(1e-9, sum(x["ms"] for x in ktimes.values())) for k, v in ktimes.items()}
+                            "see profiles/ for the ncu issue-slot and branch-efficiency counters" % (stats_head["node_bytes"] + stats_head["triangle_bytes"])}
+    tot_k = max(1e-9, sum(x["ms"] for x in ktimes.values()))
+    kernel_share = {k: v["ms"] / tot_k for k, v in ktimes.items()}
+    frame_hbm = sum(hbm_bytes[k] for k in ("k_trace", "k_shadow", "k_shade_surface<diffuse>"))
 
     cpu = None
     if world_size == 1 and not args.no_cpu_baseline:
@@ -366,24 +502,31 @@ def main():
                          "C++/OpenMP oracle restatement (the Rust reference cannot be built in this image)"}
 
     ref_rays = c.camera_rays + c.bounce_rays + c.shadow_rays + c.light_rays
-    step_s = wall / K
+    step_s = res["wall_ms_per_step"] * 1e-3
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W,
-        "ms_per_step": wall * 1e3 / K, "device_ms_per_step": dev_ms / K, "device_ms_per_step_instrumented": prof_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": res["wall_ms_per_step"], "device_ms_per_step": res["device_ms_per_step"], "device_ms_per_step_instrumented": prof_ms,
+        "reduce_ms_per_step": res["reduce_ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.scene}_box_{st.width}x{st.height}_{spp}spp_pt (BASELINE configs[0]: data/config_test_cornell_box.toml, PT, 1080p @ 16 spp)",
                    "spp_per_gpu": spp, "total_spp": total_spp, "max_bounces": st.max_bounces, "min_bounces": st.min_bounces,
-                   "light_samples": st.light_samples, "parallelism": f"spp-split x{world_size} + 1 NCCL film reduce",
-                   "cache_note": "inputs larger than L2: one wave streams %.1f GB of queue records" % (wh * spp * 232 / 1e9)},
+                   "light_samples": st.light_samples, "parallelism": f"spp-split x{world_size} + 1 NCCL film reduce (weak scaling: {spp} spp per GPU)",
+                   "cache_note": "inputs larger than L2: one wave streams %.1f GB of queue records" % (frame_hbm / 1e9)},
         "samples_per_sec": world_size * wh * spp / step_s,
         "rays_per_sec_reference_def": world_size * ref_rays / step_s,
         "true_rays_per_sec": world_size * c.true_rays / step_s,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                 "rank0_step_ms": {"min": min(e2e_ms), "median": sorted(e2e_ms)[len(e2e_ms) // 2], "max": max(e2e_ms)}},
-        "gpu_launches": launches_all,
+        "gpu_launches": res["launches"],
         "clocks": clocks,
         "roofline": roofline,
+        "frame_hbm_roofline": {"bytes_per_step": frame_hbm, "achieved": frame_hbm / (res["device_ms_per_step"] * 1e-3) / 1e9, "unit": "GB/s",
+                               "frac": frame_hbm / (res["device_ms_per_step"] * 1e-3) / 1e9 / hbm_peak},
         "kernel_time_share": kernel_share,
+        "kernel_rooflines": roofs,
+        "strong": strong,
+        "configs": configs,
+        "multi_inprocess": multi,
         "cpu_baseline": cpu,
         "counters_last_step": c.as_dict(),
     }

@@ -1701,6 +1701,10 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
     if (wh > max_slots) return fail("film does not fit one wave");
     spp_chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(P->spp ? P->spp : 1, max_slots / wh));
   }
+  if (const char *e = std::getenv("RPT_WAVE_SLOTS_MAX")) {  // test hook: force several waves on a job that would fit one
+    size_t cap = std::strtoull(e, nullptr, 10);
+    if (cap >= wh) spp_chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(spp_chunk, cap / wh));
+  }
   size_t slots = wh * spp_chunk;
   if (int rc = ensure_wave(S, slots, slots * P->light_samples, max_bounces)) return rc;
 
