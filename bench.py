@@ -175,11 +175,19 @@ def kernel_rooflines(c, ktimes, steps, hbm_peak, l2_peak):
     # vertex / continuing-path / shadow-record counts are not split per class by the counters: the two shade kernels share the
     # figure, so per-class fractions are upper bounds on scenes that use both classes
     shade_bytes = n_vertices * (4 + 64 + 16) + (c.segments - c.camera_rays) * 64 + c.shadow_rays_traced * 36
+    # split pipeline: the vertex kernel gathers index + path + hit (84 B), writes the continuing path (64 B) and the NEE
+    # hand-over record (64 B); the NEE kernel reads the hand-over record and writes the shadow records (36 B each)
+    vertex_bytes = n_vertices * (4 + 64 + 16) + (c.segments - c.camera_rays) * 64 + c.nee_vertices * 64
+    nee_bytes = c.nee_vertices * 64 + c.shadow_rays_traced * 36
     hbm_bytes = {
         "k_trace": c.segments * (64 + 16 + 4),        # path record in, hit record + class index out
         "k_shadow": c.shadow_rays_traced * (36 + 4),  # shadow record in, one 4-byte energy RED out
         "k_shade_surface<diffuse>": shade_bytes,
         "k_shade_surface<ggx>": shade_bytes,
+        "k_shade_vertex<diffuse>": vertex_bytes,
+        "k_shade_vertex<ggx>": vertex_bytes,
+        "k_nee<diffuse>": nee_bytes,
+        "k_nee<ggx>": nee_bytes,
         "k_shade_miss": c.env_hits * (4 + 64),
     }
     bvh_bytes = {
@@ -492,7 +500,8 @@ def main():
                             "see profiles/ for the ncu issue-slot and branch-efficiency counters" % (stats_head["node_bytes"] + stats_head["triangle_bytes"])}
     tot_k = max(1e-9, sum(x["ms"] for x in ktimes.values()))
     kernel_share = {k: v["ms"] / tot_k for k, v in ktimes.items()}
-    frame_hbm = sum(hbm_bytes[k] for k in ("k_trace", "k_shadow", "k_shade_surface<diffuse>"))
+    split = any(k.startswith("k_shade_vertex") for k in ktimes)
+    frame_hbm = sum(hbm_bytes[k] for k in (("k_trace", "k_shadow", "k_shade_vertex<diffuse>", "k_nee<diffuse>") if split else ("k_trace", "k_shadow", "k_shade_surface<diffuse>")))
 
     cpu = None
     if world_size == 1 and not args.no_cpu_baseline:

@@ -220,6 +220,7 @@ typedef struct RptCounters {
   uint64_t shadow_rays_traced; /* NEE rays actually traced (zero-weight ones are skipped) */
   uint64_t walk_nodes, walk_tris, walk_insts;
   uint64_t shadow_nodes, shadow_tris, shadow_insts;
+  uint64_t nee_vertices; /* path vertices that ran NEE (non-light surface vertices when light_samples > 0) */
   double device_ms; /* device time of the call: first to last CUDA event on the library's stream */
 } RptCounters;
 

@@ -65,6 +65,9 @@ struct __align__(16) HitRec {
   float t;
   uint32_t inst, prim, pad;
 };
+struct __align__(16) NeeRec {  // NEE hand-over record of the split shade pipeline (layout: see k_shade_vertex)
+  float4 r0, r1, r2, r3;
+};
 
 // Per-bounce counters. Q_PATHS..Q_SHADOW are queue SIZES (they include the invalid entries that pad abandoned
 // chunk tails, see chunk_append); the N_* entries count valid items and feed the Profile counters.
@@ -72,7 +75,10 @@ enum : uint32_t {
   Q_PATHS = 0, Q_MISS = 1, Q_DIFFUSE = 2, Q_GGX = 3, Q_SHADOW = 4, Q_NAN = 5, Q_SHADOW_REF = 6,
   N_PATHS = 7, N_MISS = 8, N_DIFFUSE = 9, N_GGX = 10, N_SHADOW = 11,
   F_TRACE = 12, F_SHADOW = 13, F_SHADE_DIFFUSE = 14, F_SHADE_GGX = 15,  // claim counters of the dynamic tile hand-out (TileStream)
-  Q_COUNT = 16
+  Q_NEE_DIFFUSE = 16, Q_NEE_GGX = 17,  // sizes of the two NEE hand-over queues (split shade pipeline), padding included
+  N_NEE = 18,                          // valid NEE hand-over records (both classes)
+  F_NEE_DIFFUSE = 19, F_NEE_GGX = 20,
+  Q_COUNT = 24
 };
 
 struct RenderCtx {
@@ -89,6 +95,7 @@ struct WaveBuffers {
   PathRec *paths[2];
   HitRec *hits;
   uint32_t *q_miss, *q_diffuse, *q_ggx;
+  NeeRec *nee_d, *nee_g;  // NEE hand-over queues, one per material class
   float4 *sh_a, *sh_b;  // shadow records: (origin.xyz, pre-contribution), (dir.xyz, lambda)
   uint32_t *sh_c;       // slot | kind << 31 (1 = environment any-hit)
   float *acc;           // per-slot energy (pt.rs `sum.energy`)
@@ -794,6 +801,307 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
   flush_count(n_nan, counts + Q_NAN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Split shade pipeline (default): k_shade_surface above cut in two at the point where the walk and the NEE part ways.
+//   k_shade_vertex<CLASS> : gather path + hit, rebuild the hit, sample the BSDF, russian roulette, light-hit MIS,
+//                           write the next path record; a vertex that wants NEE leaves a 64-byte hand-over record
+//   k_nee<CLASS>          : reads the hand-over records (compact, sequential), draws the L light / environment samples,
+//                           evaluates the BSDF and the MIS weight, appends the shadow rays
+// Why (ncu, profiles/r01_final_ncu_kernels.csv + r02 captures): the fused kernel is 6 640 SASS instructions of which a
+// vertex executes ~2 750; at 72 registers it spills 116 B, reaches 37 % occupancy and its top stall is instruction fetch
+// (the ~35 KB straight-line path of one vertex overruns the instruction cache). Each half is about half as long, fits
+// 64 registers (8 CTAs / SM, 50 % occupancy) and the NEE half reads a dense queue, so none of its lanes idle on vertices
+// that hit a light or produced a NaN pdf. Cost: 64 B written + 64 B read per NEE vertex.
+// Hand-over record, 4 x float4:
+//   r0 = vertex point.xyz, beta              r1 = shading normal.xyz, lambda
+//   r2 = wi (local, towards the previous vertex).xyz, slot bits
+//   r3 = diffuse: albedo, -, -, -            ggx: eta_inner, eta_outer, kappa, material index bits
+// The tangent frame is rebuilt from the normal (frame_from_normal is a pure function of it), pixel / sample from the slot.
+template <uint32_t CLASS>
+__global__ void __launch_bounds__(SHADE_THREADS, 8) k_shade_vertex(DevScene S, RenderCtx R, uint32_t bounce, const PathRec *__restrict__ paths,
+                                                                  const HitRec *__restrict__ hits, const uint32_t *__restrict__ queue,
+                                                                  uint32_t *__restrict__ counts, uint32_t *__restrict__ next_counts,
+                                                                  PathRec *__restrict__ out, NeeRec *__restrict__ nee, float *__restrict__ acc) {
+  // software-pipelined gather, as in k_shade_surface: [stage][float4 k][thread]
+  __shared__ float4 s_stage[2][5][SHADE_THREADS];
+  const uint32_t n = counts[CLASS];
+  const uint32_t n_round = (n + 31u) & ~31u;
+  const uint32_t L = R.light_samples;
+  const uint32_t max_bounces = R.only_direct ? 1u : R.max_bounces;
+  const uint32_t tid = threadIdx.x;
+  auto issue = [&](int stage, uint32_t idx) {
+    if (idx != RPT_NONE) {
+      const float4 *rp = reinterpret_cast<const float4 *>(paths + idx);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cp_async16(&s_stage[stage][k][tid], rp + k);
+      cp_async16(&s_stage[stage][4][tid], hits + idx);
+    }
+    cp_async_commit();
+  };
+  WarpChunk wc_next = chunk_init(), wc_nee = chunk_init();
+  uint32_t n_next = 0, n_nee = 0, n_nan = 0;
+  auto mark_next = [&](uint32_t e) { out[e].r3 = make_float4(__uint_as_float(RPT_NONE), 0.0f, 0.0f, 0.0f); };
+  auto mark_nee = [&](uint32_t e) { nee[e].r2 = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RPT_NONE)); };
+  uint32_t *nee_counter = counts + (CLASS == Q_DIFFUSE ? Q_NEE_DIFFUSE : Q_NEE_GGX);
+  const uint32_t lane = tid & 31u;
+  const uint32_t n_tiles = n_round >> 5;
+  TileStream ts;
+  ts.init(counts + (CLASS == Q_DIFFUSE ? F_SHADE_DIFFUSE : F_SHADE_GGX), n_tiles, gridDim.x * (SHADE_THREADS / 32), S.min_grab);
+  auto tile_idx = [&](uint32_t t) -> uint32_t {
+    uint32_t i = t * 32u + lane;
+    return (t != RPT_NONE && i < n) ? __ldg(queue + i) : RPT_NONE;
+  };
+  uint32_t t_cur = ts.next(), t_next = ts.next();
+  uint32_t idx_cur = tile_idx(t_cur), idx_next = tile_idx(t_next);
+  issue(0, idx_cur);
+  int stage = 0;
+  while (t_cur != RPT_NONE) {
+    issue(stage ^ 1, idx_next);  // prefetch the next item while this one is shaded
+    uint32_t t_nn = ts.next();
+    uint32_t idx_nn = tile_idx(t_nn);
+    cp_async_wait<1>();  // everything but the group just committed has landed
+    bool active = idx_cur != RPT_NONE;  // beyond the queue, or chunk padding
+    // Three phases, so that no output record has to sit in registers across the warp-wide queue reservations:
+    // (1) evaluate the vertex and decide what it emits, (2) reserve the queue entries (warp-uniform), (3) build each
+    // record and store it straight to its entry.
+    bool continues = false, do_nee = false;
+    float3 hp = f3(0, 0, 0), hn = f3(0, 0, 1), wo = f3(0, 0, 1), prev_p = f3(0, 0, 0);
+    float beta = 0.0f, lambda = 0.0f, pdf_forward = 0.0f, nbeta = 0.0f;
+    uint32_t slot = 0;
+    float4 extra = make_float4(0, 0, 0, 0);
+    if (active) {
+      PathRec r;
+      r.r0 = s_stage[stage][0][tid];
+      r.r1 = s_stage[stage][1][tid];
+      r.r2 = s_stage[stage][2][tid];
+      r.r3 = s_stage[stage][3][tid];
+      float4 hraw = s_stage[stage][4][tid];
+      TraceHit th;
+      th.t = hraw.x;
+      th.inst = __float_as_uint(hraw.y);
+      th.prim = __float_as_uint(hraw.z);
+      prev_p = f3(r.r0);
+      float3 prev_n = f3(r.r1), d = f3(r.r2);
+      float prev_pdf = r.r1.w;
+      beta = r.r0.w;
+      lambda = r.r2.w;
+      slot = __float_as_uint(r.r3.x);
+      float3 o = rec_origin(r);
+      SurfaceHit sh;
+      reconstruct_hit(S, o, d, th, sh);
+      hp = sh.p;
+      hn = sh.n;
+      Frame frame = frame_from_normal(sh.n);
+      float3 wi = normalized(to_local(frame, -d));  // integrator/utils.rs:175-176
+      const RptMaterial m = S.materials[RPT_MAT_INDEX(sh.material)];
+      const uint32_t pixel = slot % R.wh, sample = R.sample_base + slot / R.wh;
+      RptRand4 s = rpt_philox(R.seed, pixel, sample, rpt_block_bsdf(bounce, L));
+
+      // ---- generate_and_evaluate
+      float f, pdf;
+      if (CLASS == Q_GGX) {
+        GgxParams gp = ggx_params(S, m, lambda);
+        Bsdf b = ggx_generate_and_evaluate(gp, s.x, s.y, wi, wo);
+        f = b.f;
+        pdf = b.pdf;
+        extra = make_float4(gp.eta_inner, gp.eta_outer, gp.kappa, __uint_as_float(RPT_MAT_INDEX(sh.material)));
+      } else {
+        float albedo = diffuse_albedo(S, m, lambda, sh.u, sh.v);
+        wo = random_cosine_direction(s.x, s.y) * signumf(wi.z);
+        f = albedo / RPT_PI;
+        pdf = fabsf(wo.z) / RPT_PI;
+        extra.x = albedo;
+      }
+      if (pdf != pdf) {
+        // pdf NaN: the walk breaks BEFORE pushing the vertex (integrator/utils.rs:261-263)
+        n_nan++;
+      } else {
+        // ---- the vertex exists: its contribution (second loop of pt.rs:481-613)
+        if (RPT_MAT_IS_LIGHT(sh.material)) {
+          float emission = material_emission(S, m, lambda, wi);
+          if (emission > 0.0f) {
+            float c = 0.0f;
+            if (L == 0 || bounce == 0) {
+              c = beta * emission;
+            } else if (!R.only_direct) {
+              float3 nee_direction = normalized(sh.p - prev_p);
+              float hyp = instance_psa_pdf(S.instances[th.inst], dot(prev_n, nee_direction), dot(sh.n, nee_direction), prev_p, sh.p);
+              c = power_heuristic(prev_pdf, hyp) * beta * emission;
+            }
+            if (c != 0.0f) atomicAdd(acc + slot, c);
+          }
+        } else if (L > 0) {
+          do_nee = true;
+        }
+        // ---- continue the walk (integrator/utils.rs:266-329)
+        float cos_o = fabsf(wo.z);
+        float rr = bounce >= R.min_bounces ? fminf(f / pdf, 1.0f) : 1.0f;
+        pdf_forward = pdf * (rr / cos_o);
+        nbeta = beta * (f / pdf_forward);
+        if (pdf_forward == 0.0f) nbeta = 0.0f;
+        continues = nbeta != 0.0f && !(s.z > rr) && bounce + 1 < max_bounces;
+      }
+    }
+    const uint32_t k_next = chunk_append(next_counts + Q_PATHS, wc_next, continues, mark_next);
+    const uint32_t k_nee = chunk_append(nee_counter, wc_nee, do_nee, mark_nee);
+    n_next += continues;
+    n_nee += do_nee;
+    if (continues || do_nee) {
+      const Frame frame = frame_from_normal(hn);  // (a pure function of the normal: the same frame as above)
+      if (continues) {
+        float3 nd = normalized(to_world(frame, wo));
+        float4 *o4 = reinterpret_cast<float4 *>(out + k_next);
+        o4[0] = make_float4(hp.x, hp.y, hp.z, nbeta);
+        o4[1] = make_float4(hn.x, hn.y, hn.z, pdf_forward);
+        o4[2] = make_float4(nd.x, nd.y, nd.z, lambda);
+        o4[3] = make_float4(__uint_as_float(slot), signumf(wo.z), 0.0f, 0.0f);
+      }
+      if (do_nee) {
+        float3 wi_nee = to_local(frame, normalized(prev_p - hp));  // pt.rs:565-569
+        float4 *n4 = reinterpret_cast<float4 *>(nee + k_nee);
+        n4[0] = make_float4(hp.x, hp.y, hp.z, beta);
+        n4[1] = make_float4(hn.x, hn.y, hn.z, lambda);
+        n4[2] = make_float4(wi_nee.x, wi_nee.y, wi_nee.z, __uint_as_float(slot));
+        n4[3] = extra;
+      }
+    }
+    stage ^= 1;
+    idx_cur = idx_next;
+    idx_next = idx_nn;
+    t_cur = t_next;
+    t_next = t_nn;
+  }
+  cp_async_wait<0>();
+  if (wc_next.used < QCHUNK) chunk_pad(wc_next, mark_next);
+  if (wc_nee.used < QCHUNK) chunk_pad(wc_nee, mark_nee);
+  flush_count(n_next, next_counts + N_PATHS);
+  flush_count(n_nee, counts + N_NEE);
+  flush_count(n_nan, counts + Q_NAN);
+}
+
+// NEE sample generation for the vertices k_shade_vertex handed over (estimate_direct_illumination_with_loop, pt.rs:333-393;
+// light samples pt.rs:146-219, environment samples pt.rs:224-331). One vertex per lane, L samples each; every sample that
+// can contribute becomes a shadow ray, appended binned by origin cell (see k_shade_surface).
+template <uint32_t CLASS>
+__global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx R, uint32_t bounce, const NeeRec *__restrict__ nee,
+                                                         uint32_t *__restrict__ counts, float4 *__restrict__ sh_a, float4 *__restrict__ sh_b,
+                                                         uint32_t *__restrict__ sh_c) {
+  __shared__ WarpChunk s_chunks[SHADE_THREADS / 32][NBINS];
+  WarpChunk *st_shadow = s_chunks[threadIdx.x >> 5];
+  if ((threadIdx.x & 31u) < NBINS) st_shadow[threadIdx.x & 31u] = WarpChunk{0u, QCHUNK_BINNED};
+  __syncwarp();
+  const uint32_t n = counts[CLASS == Q_DIFFUSE ? Q_NEE_DIFFUSE : Q_NEE_GGX];
+  const uint32_t L = R.light_samples;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n_tiles = (n + 31u) >> 5;
+  const uint32_t nbins = n >= BIN_MIN_ITEMS ? NBINS : 1u;  // small queues: binning would only scatter a few rays over many chunks
+  uint32_t n_shadow = 0, n_sh_ref = 0;
+  auto mark_shadow = [&](uint32_t e) { sh_c[e] = RPT_NONE; };
+  const float inv_l = 1.0f / (float)L;
+  TileStream ts;
+  ts.init(counts + (CLASS == Q_DIFFUSE ? F_NEE_DIFFUSE : F_NEE_GGX), n_tiles, gridDim.x * (SHADE_THREADS / 32), S.min_grab);
+  for (uint32_t tile = ts.next(); tile != RPT_NONE; tile = ts.next()) {
+    const uint32_t i = tile * 32u + lane;
+    bool do_nee = i < n;
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = make_float4(0, 0, 1, 0), r2 = make_float4(0, 0, 1, 0), r3 = make_float4(0, 0, 0, 0);
+    if (do_nee) {
+      const float4 *rp = reinterpret_cast<const float4 *>(nee + i);
+      r2 = __ldg(rp + 2);
+      do_nee = __float_as_uint(r2.w) != RPT_NONE;  // chunk padding
+      if (do_nee) {
+        r0 = __ldg(rp);
+        r1 = __ldg(rp + 1);
+        r3 = __ldg(rp + 3);
+      }
+    }
+    const float3 p = f3(r0), nrm = f3(r1), wi_nee = f3(r2);
+    const float beta = r0.w, lambda = r1.w;
+    const uint32_t slot = __float_as_uint(r2.w);
+    const uint32_t pixel = slot % R.wh, sample = R.sample_base + slot / R.wh;
+    const Frame frame = frame_from_normal(nrm);
+    GgxParams gp;
+    gp.alpha = 1.0f;
+    gp.eta_inner = r3.x;
+    gp.eta_outer = r3.y;
+    gp.kappa = r3.z;
+    gp.metallic = false;
+    if (CLASS == Q_GGX && do_nee) {
+      const RptMaterial &m = S.materials[__float_as_uint(r3.w)];
+      gp.alpha = m.alpha;
+      gp.metallic = m.metallic != 0;
+    }
+    const float albedo = r3.x;
+    for (uint32_t ls = 0; ls < L; ++ls) {
+      bool has = false;
+      float4 a = make_float4(0, 0, 0, 0), b4 = make_float4(0, 0, 0, 0);
+      uint32_t c = 0;
+      if (do_nee) {
+        RptRand4 sn = rpt_philox(R.seed, pixel, sample, rpt_block_nee(bounce, L, ls));
+        float pick;
+        bool sample_world = choose(sn.x, S.p_env, pick);  // pt.rs:350-353
+        float3 dir = f3(0, 0, 1);
+        float light_pdf = 0.0f, emission = 1.0f;
+        bool valid = true;
+        if (sample_world) {
+          float eu, ev;
+          env_sample_uv(S, sn.y, sn.z, eu, ev, light_pdf);
+          dir = uv_to_direction(eu, ev);
+          emission = env_emission(S, eu, ev, lambda);
+        } else {
+          valid = S.num_lights > 0;
+          if (valid) {
+            uint32_t li = (uint32_t)clampf((float)S.num_lights * pick, 0.0f, (float)S.num_lights - 1.0f);  // world/mod.rs:109
+            instance_sample(S.instances[S.lights[li]], sn.y, sn.z, p, dir, light_pdf);
+            light_pdf = light_pdf * (1.0f / (float)S.num_lights);
+            valid = light_pdf != 0.0f;  // pt.rs:151-153
+          }
+        }
+        float3 local_wo = to_local(frame, dir);
+        if (sample_world && local_wo.z <= 0.0f) valid = false;  // pt.rs:245-247
+        if (valid) {
+          Bsdf bs;
+          if (CLASS == Q_GGX) {
+            bs = ggx_bsdf(gp, wi_nee, local_wo);
+          } else {  // lambertian.rs:16-32 / diffuse_light.rs:29-45
+            bool same = local_wo.z * wi_nee.z > 0.0f;
+            bs.f = same ? albedo / RPT_PI : 0.0f;
+            bs.pdf = same ? fabsf(local_wo.z) / RPT_PI : 0.0f;
+          }
+          n_sh_ref++;  // the reference traces (and counts) this ray whatever its weight
+          float weight = R.only_direct ? 1.0f : power_heuristic_generic(light_pdf, bs.pdf);
+          float pre;
+          float3 so;
+          if (sample_world) {
+            pre = beta * weight * bs.f * emission * fabsf(local_wo.z) * (1.0f / light_pdf) * inv_l;  // pt.rs:313-318
+            so = p + (nrm * RPT_NORMAL_OFFSET) * signumf(dir.z);  // WORLD z (quirk Q12, pt.rs:256)
+            c = slot | 0x80000000u;
+          } else {
+            pre = bs.f * beta * fabsf(local_wo.z) * weight / light_pdf * inv_l;  // pt.rs:196-202 minus the light-side terms
+            so = p + (nrm * RPT_NORMAL_OFFSET) * signumf(local_wo.z);  // pt.rs:171-174
+            c = slot;
+          }
+          if (pre != 0.0f) {  // a zero pre-factor cannot contribute: skip the visibility query
+            has = true;
+            a = make_float4(so.x, so.y, so.z, pre);
+            b4 = make_float4(dir.x, dir.y, dir.z, lambda);
+          }
+        }
+      }
+      uint32_t bin_sh = nbins > 1 ? ((a.x < S.world_center.x) | ((a.y < S.world_center.y) << 1) | ((a.z < S.world_center.z) << 2)) : 0u;  // origin cell
+      uint32_t q = chunk_append_binned(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow);
+      if (has) {
+        sh_a[q] = a;
+        sh_b[q] = b4;
+        sh_c[q] = c;
+      }
+      n_shadow += has;
+    }
+  }
+  chunk_pad_binned(st_shadow, NBINS, mark_shadow);
+  flush_count(n_shadow, counts + N_SHADOW);
+  flush_count(n_sh_ref, counts + Q_SHADOW_REF);  // reference-definition shadow-ray counter (pt.rs:176,252)
+}
+
 // Phase A of the two-phase NEE visibility query: the closest hit among the scene's few analytic light-material shapes
 // (DevScene::light_geom), with the reference's tie rule. Returns false when the ray meets none of them.
 template <bool STATS>
@@ -1289,8 +1597,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32
 // ---------------------------------------------------------------------------------------------
 // host side: scene upload + wave driver
 // ---------------------------------------------------------------------------------------------
-enum KernelId { K_RAYGEN, K_TRACE, K_SHADE_MISS, K_SHADE_DIFFUSE, K_SHADE_GGX, K_SHADOW, K_FILM, K_NUM };
-const char *kKernelNames[K_NUM] = {"k_raygen", "k_trace", "k_shade_miss", "k_shade_surface<diffuse>", "k_shade_surface<ggx>", "k_shadow", "k_film"};
+// K_SHADE_*: k_shade_vertex<> of the split pipeline, or the fused k_shade_surface<> (RPT_FUSED_SHADE=1); K_NEE_*: k_nee<>
+enum KernelId { K_RAYGEN, K_TRACE, K_SHADE_MISS, K_SHADE_DIFFUSE, K_SHADE_GGX, K_NEE_DIFFUSE, K_NEE_GGX, K_SHADOW, K_FILM, K_NUM };
+const char *kKernelNamesSplit[K_NUM] = {"k_raygen", "k_trace", "k_shade_miss", "k_shade_vertex<diffuse>", "k_shade_vertex<ggx>", "k_nee<diffuse>", "k_nee<ggx>", "k_shadow", "k_film"};
+const char *kKernelNamesFused[K_NUM] = {"k_raygen", "k_trace", "k_shade_miss", "k_shade_surface<diffuse>", "k_shade_surface<ggx>", "-", "-", "k_shadow", "k_film"};
 
 // Scene arrays are sub-allocated from one device block (small scenes: a single 4 MB block that is handed from scene to
 // scene through a per-device spare, so a create / render / destroy frame loop issues no cudaMalloc / cudaFree for them:
@@ -1379,6 +1689,7 @@ struct RptScene {
   size_t stack_smem = 0;
   uint32_t env_stack_count = 0;  // textures in the environment's stack (HDR)
   bool has_ggx = true;     // any material of the GGX class (else its shade kernel is never launched)
+  bool fused_shade = false;  // RPT_FUSED_SHADE=1: the round-1 single shade kernel instead of k_shade_vertex + k_nee
   int trav_mode = TRAV_BVH;  // TRAV_SMALL (RPT_SMALL=1) for scenes of <= RPT_SMALL_MAX leaves without a BLAS;
                              // TRAV_BVH_TMA: k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
   size_t counts_cap = 0;     // bounces the per-bounce counter block has room for
@@ -1464,7 +1775,7 @@ struct WaveCache {
 WaveCache g_wave_cache[64];
 
 void release_wave_buffers(WaveBuffers &w) {
-  void *ptrs[] = {w.paths[0], w.paths[1], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.sh_a, w.sh_b, w.sh_c, w.acc, w.counts, w.work};
+  void *ptrs[] = {w.paths[0], w.paths[1], w.hits, w.q_miss, w.q_diffuse, w.q_ggx, w.nee_d, w.nee_g, w.sh_a, w.sh_b, w.sh_c, w.acc, w.counts, w.work};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   w = WaveBuffers{};
@@ -1481,18 +1792,18 @@ int free_wave(RptScene *S) {
 // overflow (a warp that cannot fit its <= 32 new entries pads the tail and takes a fresh chunk), and at kernel end every
 // warp abandons at most one chunk per queue (per bin for the binned shadow queue). The next-path and shadow queues are
 // appended to by both shade kernels (diffuse, ggx); the class lists by k_trace.
-size_t path_queue_cap(const RptScene *S, size_t valid) {
+size_t path_queue_cap(const RptScene *S, size_t valid) {  // next-path queue, class lists, NEE hand-over queues
   size_t shade_warps = ((size_t)S->grid[K_SHADE_DIFFUSE] + (size_t)S->grid[K_SHADE_GGX]) * (SHADE_THREADS / 32);
   size_t trace_warps = (size_t)S->grid[K_TRACE] * (TRACE_THREADS / 32);
   size_t tail = std::max(shade_warps, trace_warps) * QCHUNK;
   return valid + (valid * 31 + (QCHUNK - 31) - 1) / (QCHUNK - 31) + tail + QCHUNK;
 }
 size_t shadow_queue_cap(const RptScene *S, size_t valid) {
-  size_t shade_warps = ((size_t)S->grid[K_SHADE_DIFFUSE] + (size_t)S->grid[K_SHADE_GGX]) * (SHADE_THREADS / 32);
+  size_t shade_warps = ((size_t)std::max(S->grid[K_SHADE_DIFFUSE], S->grid[K_NEE_DIFFUSE]) + (size_t)std::max(S->grid[K_SHADE_GGX], S->grid[K_NEE_GGX])) * (SHADE_THREADS / 32);
   size_t tail = shade_warps * NBINS * QCHUNK_BINNED;
   return valid + (valid * 31 + (QCHUNK_BINNED - 31) - 1) / (QCHUNK_BINNED - 31) + tail + QCHUNK_BINNED;
 }
-constexpr size_t kPathSlotBytes = 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t);
+constexpr size_t kPathSlotBytes = 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t) + 2 * sizeof(NeeRec);
 constexpr size_t kShadowSlotBytes = 2 * sizeof(float4) + sizeof(uint32_t);
 size_t wave_bytes(const RptScene *S, size_t slots, uint32_t light_samples) {
   return path_queue_cap(S, slots) * kPathSlotBytes + shadow_queue_cap(S, slots * light_samples) * kShadowSlotBytes + slots * sizeof(float);
@@ -1551,6 +1862,8 @@ int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid, size_t bounces) 
   CUDA_TRY(cudaMalloc(&w.q_miss, pcap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&w.q_diffuse, pcap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&w.q_ggx, pcap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&w.nee_d, pcap * sizeof(NeeRec)));
+  CUDA_TRY(cudaMalloc(&w.nee_g, pcap * sizeof(NeeRec)));
   CUDA_TRY(cudaMalloc(&w.sh_a, scap * sizeof(float4)));
   CUDA_TRY(cudaMalloc(&w.sh_b, scap * sizeof(float4)));
   CUDA_TRY(cudaMalloc(&w.sh_c, scap * sizeof(uint32_t)));
@@ -1761,13 +2074,34 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
         k_shade_miss<<<S->grid[K_SHADE_MISS], 256, 0, S->stream>>>(S->dev, in, w.q_miss, cb, w.acc);
         T.end();
       }
-      T.begin(K_SHADE_DIFFUSE);
-      k_shade_surface<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
-      T.end();
-      if (S->has_ggx) {  // (no GGX material in the scene: the class list stays empty, skip its 12 launches per wave)
-        T.begin(K_SHADE_GGX);
-        k_shade_surface<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
+      if (S->fused_shade) {
+        T.begin(K_SHADE_DIFFUSE);
+        k_shade_surface<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
         T.end();
+        if (S->has_ggx) {  // (no GGX material in the scene: the class list stays empty, skip its 12 launches per wave)
+          T.begin(K_SHADE_GGX);
+          k_shade_surface<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
+          T.end();
+        }
+      } else {
+        T.begin(K_SHADE_DIFFUSE);
+        k_shade_vertex<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.nee_d, w.acc);
+        T.end();
+        if (S->has_ggx) {
+          T.begin(K_SHADE_GGX);
+          k_shade_vertex<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.nee_g, w.acc);
+          T.end();
+        }
+        if (P->light_samples > 0) {
+          T.begin(K_NEE_DIFFUSE);
+          k_nee<Q_DIFFUSE><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
+          T.end();
+          if (S->has_ggx) {
+            T.begin(K_NEE_GGX);
+            k_nee<Q_GGX><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
+            T.end();
+          }
+        }
       }
       if (P->light_samples > 0) {
         T.begin(K_SHADOW);
@@ -1792,6 +2126,7 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       C.bounce_rays += c[N_MISS] + c[N_DIFFUSE] + c[N_GGX] - c[Q_NAN];
       C.shadow_rays += c[Q_SHADOW_REF];
       C.shadow_rays_traced += c[N_SHADOW];
+      C.nee_vertices += c[N_NEE];
     }
   }
   size_t ev_last = S->ev_used;
@@ -2270,8 +2605,20 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
   }
   S->grid[K_SHADE_MISS] = occupancy_grid(k_shade_miss, 256, 0, S->num_sms);
-  S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_surface<Q_DIFFUSE>, SHADE_THREADS, 0, S->num_sms);
-  S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_surface<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
+  {
+    const char *e = std::getenv("RPT_FUSED_SHADE");
+    S->fused_shade = e && e[0] == '1';
+  }
+  if (S->fused_shade) {
+    S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_surface<Q_DIFFUSE>, SHADE_THREADS, 0, S->num_sms);
+    S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_surface<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
+    S->grid[K_NEE_DIFFUSE] = S->grid[K_NEE_GGX] = 0;
+  } else {
+    S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_vertex<Q_DIFFUSE>, SHADE_THREADS, 0, S->num_sms);
+    S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_vertex<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
+    S->grid[K_NEE_DIFFUSE] = occupancy_grid(k_nee<Q_DIFFUSE>, SHADE_THREADS, 0, S->num_sms);
+    S->grid[K_NEE_GGX] = occupancy_grid(k_nee<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
+  }
   S->grid[K_FILM] = occupancy_grid(k_film, 256, film_smem, S->num_sms);
   lap("occupancy queries");
   *out = S;
@@ -2441,7 +2788,7 @@ int rpt_last_kernel_times(RptScene *S, RptKernelTime *out, uint32_t cap, uint32_
   uint32_t k = 0;
   for (int i = 0; i < K_NUM && k < cap; ++i) {
     if (S->kernel_launches[i] == 0) continue;
-    out[k].name = kKernelNames[i];
+    out[k].name = S->fused_shade ? kKernelNamesFused[i] : kKernelNamesSplit[i];
     out[k].launches = S->kernel_launches[i];
     out[k].ms = S->kernel_ms[i];
     ++k;

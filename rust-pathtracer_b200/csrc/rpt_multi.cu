@@ -145,12 +145,14 @@ int rpt_multi_destroy(RptMulti *M) {
   for (int i = 0; i < (int)M->comms.size(); ++i)
     if (M->comms[i]) M->nccl.CommDestroy(M->comms[i]);
   for (int i = 0; i < (int)M->scenes.size(); ++i) {
+    if (!M->scenes[i]) continue;  // (a device the scene could not be created on: possibly not a valid ordinal at all)
     cudaSetDevice(M->devices[i]);
     if (i < (int)M->streams.size() && M->streams[i]) cudaStreamDestroy(M->streams[i]);
     if (i < (int)M->ev0.size() && M->ev0[i]) cudaEventDestroy(M->ev0[i]);
     if (i < (int)M->ev1.size() && M->ev1[i]) cudaEventDestroy(M->ev1[i]);
-    if (M->scenes[i]) rpt_scene_destroy(M->scenes[i]);
+    rpt_scene_destroy(M->scenes[i]);
   }
+  cudaGetLastError();  // nothing here may leave a stale error behind for the next call's cudaGetLastError() check
   delete M;
   return 0;
 }
@@ -342,6 +344,7 @@ int rpt_multi_render_pt(RptMulti *M, const RptRenderParams *P, float *film_xyzw,
     T.camera_rays += c.camera_rays; T.bounce_rays += c.bounce_rays; T.shadow_rays += c.shadow_rays; T.light_rays += c.light_rays;
     T.env_hits += c.env_hits; T.segments += c.segments; T.true_rays += c.true_rays; T.kernel_launches += c.kernel_launches;
     T.shadow_rays_traced += c.shadow_rays_traced;
+    T.nee_vertices += c.nee_vertices;
     T.walk_nodes += c.walk_nodes; T.walk_tris += c.walk_tris; T.walk_insts += c.walk_insts;
     T.shadow_nodes += c.shadow_nodes; T.shadow_tris += c.shadow_tris; T.shadow_insts += c.shadow_insts;
     render_ms_max = std::max(render_ms_max, c.device_ms);

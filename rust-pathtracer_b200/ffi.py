@@ -110,7 +110,7 @@ class RptCounters(ct.Structure):
         ("camera_rays", c_u64), ("bounce_rays", c_u64), ("shadow_rays", c_u64), ("light_rays", c_u64),
         ("env_hits", c_u64), ("segments", c_u64), ("true_rays", c_u64), ("kernel_launches", c_u64),
         ("shadow_rays_traced", c_u64), ("walk_nodes", c_u64), ("walk_tris", c_u64), ("walk_insts", c_u64),
-        ("shadow_nodes", c_u64), ("shadow_tris", c_u64), ("shadow_insts", c_u64), ("device_ms", ct.c_double),
+        ("shadow_nodes", c_u64), ("shadow_tris", c_u64), ("shadow_insts", c_u64), ("nee_vertices", c_u64), ("device_ms", ct.c_double),
     ]
 
     def as_dict(self) -> dict:

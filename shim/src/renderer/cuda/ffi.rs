@@ -217,6 +217,7 @@ pub struct RptCounters {
     pub shadow_nodes: u64,
     pub shadow_tris: u64,
     pub shadow_insts: u64,
+    pub nee_vertices: u64,
     pub device_ms: f64,
 }
 
@@ -343,7 +344,7 @@ mod tests {
         assert_eq!(size_of::<RptCamera>(), 100);
         assert_eq!(size_of::<RptSceneDesc>(), 376);
         assert_eq!(size_of::<RptRenderParams>(), 64);
-        assert_eq!(size_of::<RptCounters>(), 128);
+        assert_eq!(size_of::<RptCounters>(), 136);
         assert_eq!(size_of::<RptSceneStats>(), 56);
         assert_eq!(size_of::<RptOutputSettings>(), 28);
         assert_eq!(size_of::<RptImapBake>(), 40);

@@ -5,5 +5,6 @@ rep="$1"; name="$2"; shift 2
 python tools/ncu_summary.py "$rep" "gpurun_out/${name}_kernels.csv" > /dev/null 2>&1
 ncu -i "$rep" --page raw --csv 2>/dev/null | gzip -9 > "gpurun_out/${name}_raw.csv.gz"
 for id in "$@"; do
-  ncu -i "$rep" --page source --csv --kernel-id :::$id 2>/dev/null | gzip -9 > "gpurun_out/${name}_source_k${id}.csv.gz"
+  ncu -i "$rep" --page source --csv --print-source sass --kernel-id :::$id 2>/dev/null | gzip -9 > "gpurun_out/${name}_source_k${id}.csv.gz"
+  ncu -i "$rep" --page source --csv --print-source cuda --kernel-id :::$id 2>/dev/null | gzip -9 > "gpurun_out/${name}_cuda_k${id}.csv.gz"
 done

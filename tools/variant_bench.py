@@ -16,5 +16,5 @@ for so in sys.argv[2:]:
         kt = {k["name"]: k["ms"] for k in sc.kernel_times()}
         if best is None or cnt.device_ms < best[0]:
             best = (cnt.device_ms, kt, cnt.segments)
-    print(f"{so:28s} {best[0]:8.2f} ms  {best[2] / best[0] / 1e6:6.3f} Gseg/s  trace {best[1].get('k_trace', 0):7.2f} shadow {best[1].get('k_shadow', 0):7.2f} shade {best[1].get('k_shade_surface<diffuse>', 0):7.2f} ggx {best[1].get('k_shade_surface<ggx>', 0):7.2f}")
+    print(f"{so:28s} {best[0]:8.2f} ms  {best[2] / best[0] / 1e6:6.3f} Gseg/s  trace {best[1].get('k_trace', 0):7.2f} shadow {best[1].get('k_shadow', 0):7.2f} shade {best[1].get('XX")
     sc.close()
