@@ -346,7 +346,17 @@ __device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t m
 // Closest-hit traversal of the path queue; appends each path to the list of its vertex's class.
 // RAYGEN: the launch of bounce 0 generates its camera vertices itself (and writes them out for the shade kernel) instead
 // of reading what a separate ray-generation kernel wrote: one 64-byte queue write + read per sample less.
-enum : int { TRAV_BVH = 0, TRAV_BVH_TMA = 1, TRAV_SMALL = 2 };  // how the traversal kernels find hits (chosen per scene)
+enum : int { TRAV_BVH = 0, TRAV_BVH_TMA = 1, TRAV_SMALL = 2, TRAV_BVH_REFILL = 3 };  // how the traversal kernels find hits (chosen per scene)
+
+// TRAV_BVH_REFILL: lanes whose ray has finished are re-armed with the next ray of the queue while the other lanes of the
+// warp are still walking ("persistent threads with dynamic fetch", Aila & Laine 2009), once at least REFILL_MIN lanes are
+// idle. Why: on the 10 M-triangle instanced scene every part of the traversal kernels - node loop, leaf code, instance
+// entry - runs at 6.5-7.7 of 32 lanes (ncu source view, profiles/r02_pre_monkeys_*): rays take 5 to 100+ node visits, a warp
+// lives as long as its longest ray, and the lanes of the short rays idle. (Round 1 measured the same idea on the Cornell
+// box, where rays are 7-9 nodes long and there is nothing to recover.)
+#ifndef REFILL_MIN
+#define REFILL_MIN 8u
+#endif
 
 // Copies the small-scene triangle table into the CTA's dynamic shared memory (TRAV_SMALL only).
 __device__ __forceinline__ void stage_small_tris(const DevScene &S, float4 *s_tris) {
@@ -489,7 +499,106 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
     n_diffuse += cls == Q_DIFFUSE;
     n_ggx += cls == Q_GGX;
   };
-  if (TMA || (!TRACE_DYNAMIC && MODE != TRAV_SMALL)) {
+  if (MODE == TRAV_BVH_REFILL) {
+    const PathRec *src = RAYGEN ? paths_out : paths;
+    TileStream ts;
+    ts.init(counts + F_TRACE, n_tiles, total_warps, S.min_grab);
+    uint32_t pool_cur = 0, pool_end = 0, my_i = 0;  // pool: the rays of the tile the warp is handing out (warp-uniform)
+    bool has = false, exhausted = false;
+    Trav t;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    while (true) {
+      const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !has);
+      if (!exhausted && (__popc(idle) >= REFILL_MIN || idle == 0xFFFFFFFFu)) {
+        const uint32_t need = __popc(idle), rank = __popc(idle & lt_mask);
+        uint32_t given = 0;
+        while (given < need) {
+          if (pool_cur == pool_end) {
+            const uint32_t tile = ts.next();
+            if (tile == RPT_NONE) {
+              exhausted = true;
+              break;
+            }
+            pool_cur = tile * 32u;
+            pool_end = min(pool_cur + 32u, n);
+          }
+          const uint32_t take = min(need - given, pool_end - pool_cur);
+          if (!has && rank >= given && rank < given + take) {
+            my_i = pool_cur + (rank - given);
+            PathRec r;
+            if (RAYGEN) {
+              r = camera_record(R, my_i);
+              paths_out[my_i] = r;
+            } else {
+              const float4 *rp = reinterpret_cast<const float4 *>(paths + my_i);
+              r.r0 = __ldg(rp);
+              r.r1 = __ldg(rp + 1);
+              r.r2 = __ldg(rp + 2);
+              r.r3 = __ldg(rp + 3);
+            }
+            if (__float_as_uint(r.r3.x) != RPT_NONE) {  // (padding of an abandoned chunk tail: the lane stays idle until the next hand-out)
+              t.init(S, rec_origin(r), f3(r.r2), RPT_INF);
+              has = true;
+            }
+          }
+          pool_cur += take;
+          given += take;
+        }
+      }
+      if (!__any_sync(0xFFFFFFFFu, has)) {
+        if (exhausted) break;
+        continue;  // the hand-out met only padding: take the next rays
+      }
+      bool finished = false;
+      if (has) finished = t.template step<false, STATS>(S, s_stack + threadIdx.x, TRACE_THREADS, tw);
+      if (__any_sync(0xFFFFFFFFu, finished)) {
+        uint32_t cls = RPT_NONE;
+        if (finished) {
+          has = false;
+          HitRec h;
+          h.t = t.out.t;
+          h.inst = t.out.inst;
+          h.prim = t.out.prim;
+          h.pad = 0;
+          hits[my_i] = h;
+          if (!t.found) {
+            if (S.env_kind == RPT_ENV_CONSTANT) {  // as in the tile form below, from the re-read path record
+              const float4 *rp = reinterpret_cast<const float4 *>(src + my_i);
+              float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
+              float lambda = r2.w, beta = r0.w, pdf_fwd = r1.w;
+              float emission = curve_eval(S, S.env_curve, lambda) * S.env_strength;
+              float cos_i = fabsf(dot(f3(r1), t.d));
+              float nee_psa_pdf = (1.0f / (4.0f * RPT_PI)) / fabsf(cos_i);
+              float bsdf_psa_pdf = pdf_fwd / fabsf(cos_i);
+              float c = power_heuristic(bsdf_psa_pdf, nee_psa_pdf) * beta * emission;
+              if (c != 0.0f) atomicAdd(acc + __float_as_uint(r3.x), c);
+              n_miss++;
+            } else {
+              cls = Q_MISS;
+            }
+          } else {
+            const DevInstance &I = S.instances[t.out.inst];
+            uint32_t mat = I.material;
+            if (mat == RPT_NONE) {
+              mat = RPT_MAT_PACK(RPT_MAT_TAG_MATERIAL, 0);
+              if ((I.flags & DI_KIND_MASK) == RPT_AGG_MESH) mat = __float_as_uint(__ldg(S.tri_verts + 3 * (size_t)(I.tri_base + t.out.prim)).w);
+            }
+            cls = material_class(S, mat);
+          }
+        }
+        uint32_t k;
+        k = chunk_append(counts + Q_MISS, wc_miss, cls == Q_MISS, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
+        if (cls == Q_MISS) q_miss[k] = my_i;
+        k = chunk_append(counts + Q_DIFFUSE, wc_diffuse, cls == Q_DIFFUSE, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; });
+        if (cls == Q_DIFFUSE) q_diffuse[k] = my_i;
+        k = chunk_append(counts + Q_GGX, wc_ggx, cls == Q_GGX, [&](uint32_t e) { q_ggx[e] = RPT_NONE; });
+        if (cls == Q_GGX) q_ggx[k] = my_i;
+        n_miss += cls == Q_MISS;
+        n_diffuse += cls == Q_DIFFUSE;
+        n_ggx += cls == Q_GGX;
+      }
+    }
+  } else if (TMA || (!TRACE_DYNAMIC && MODE != TRAV_SMALL)) {
     for (uint32_t tile = tile0; tile < n_tiles; tile += total_warps) body(tile);
   } else {
     TileStream ts;
@@ -1259,7 +1368,87 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
     }
     if (lit) shadow_light_contribution(S, o, d, th, pre, lambda, slot, acc);
   };
-  if (!TRACE_DYNAMIC && !SMALL) {
+  if (MODE == TRAV_BVH_REFILL) {
+    // Lane refill (see TRAV_BVH_REFILL above). A lane keeps only its queue index and the phase-A result; the record's
+    // pre-factor / wavelength / slot are re-read when the ray is finished. Both kinds of ray walk with the closest-hit step;
+    // an environment ray is finished by its first accepted hit, a two-phase light ray by the first hit that beats its light.
+    TileStream ts;
+    ts.init(counts + F_SHADOW, n_tiles, gridDim.x * (TRACE_THREADS / 32), S.min_grab);
+    uint32_t pool_cur = 0, pool_end = 0, my_i = 0, inst_l = RPT_NONE;
+    bool has = false, exhausted = false, env = false;
+    float tl = RPT_INF;
+    uint64_t key_l = 0;
+    Trav t;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool two_phase = S.num_light_geom != 0;
+    while (true) {
+      const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !has);
+      if (!exhausted && (__popc(idle) >= REFILL_MIN || idle == 0xFFFFFFFFu)) {
+        const uint32_t need = __popc(idle), rank = __popc(idle & lt_mask);
+        uint32_t given = 0;
+        while (given < need) {
+          if (pool_cur == pool_end) {
+            const uint32_t tile = ts.next();
+            if (tile == RPT_NONE) {
+              exhausted = true;
+              break;
+            }
+            pool_cur = tile * 32u;
+            pool_end = min(pool_cur + 32u, n);
+          }
+          const uint32_t take = min(need - given, pool_end - pool_cur);
+          if (!has && rank >= given && rank < given + take) {
+            my_i = pool_cur + (rank - given);
+            const uint32_t c = __ldg(sh_c + my_i);
+            if (c != RPT_NONE) {  // (chunk padding: the lane stays idle until the next hand-out)
+              const float3 o = f3(__ldg(sh_a + my_i)), d = f3(__ldg(sh_b + my_i));
+              env = (c & 0x80000000u) != 0;
+              bool go = true;
+              t.init(S, o, d, RPT_INF);
+              if (!env && two_phase) {
+                tl = RPT_INF;
+                key_l = 0;
+                inst_l = RPT_NONE;
+                go = shadow_closest_light<STATS>(S, o, d, tl, key_l, inst_l, tw);  // no light along the ray: nothing to add
+                t.closest = tl;
+                t.best_key = key_l;
+                t.found = true;
+              }
+              has = go;
+            }
+          }
+          pool_cur += take;
+          given += take;
+        }
+      }
+      if (!__any_sync(0xFFFFFFFFu, has)) {
+        if (exhausted) break;
+        continue;
+      }
+      if (has) {
+        bool finished = t.template step<false, STATS>(S, s_stack + threadIdx.x, TRACE_THREADS, tw);
+        const bool beaten = env ? t.found : (two_phase && (t.best_key != key_l || t.closest != tl));
+        if (finished || beaten) {
+          has = false;
+          const float pre = __ldg(sh_a + my_i).w, lambda = __ldg(sh_b + my_i).w;
+          const uint32_t slot = __ldg(sh_c + my_i) & 0x7FFFFFFFu;
+          if (env) {
+            if (!t.found) atomicAdd(acc + slot, pre);
+          } else {
+            TraceHit th = t.out;
+            bool lit = t.found;
+            if (two_phase) {
+              lit = !beaten;
+              th.t = tl;
+              th.inst = inst_l;
+              th.prim = 0;
+            }
+            if (lit) shadow_light_contribution(S, t.o, t.d, th, pre, lambda, slot, acc);
+          }
+        }
+      }
+    }
+  } else if (!TRACE_DYNAMIC && !SMALL) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) body(i);
   } else {
@@ -1940,6 +2129,8 @@ void launch_trace(RptScene *S, bool stats, const PathRec *in, uint32_t *cb, cons
                                                                                                w.work, w.acc, R, paths_out)
   if (S->trav_mode == TRAV_SMALL) {
     if (stats) RPT_TRACE_LAUNCH(TRAV_SMALL, true); else RPT_TRACE_LAUNCH(TRAV_SMALL, false);
+  } else if (S->trav_mode == TRAV_BVH_REFILL) {
+    if (stats) RPT_TRACE_LAUNCH(TRAV_BVH_REFILL, true); else RPT_TRACE_LAUNCH(TRAV_BVH_REFILL, false);
   } else {
     if (stats) RPT_TRACE_LAUNCH(TRAV_BVH, true); else RPT_TRACE_LAUNCH(TRAV_BVH, false);
   }
@@ -1959,6 +2150,8 @@ void launch_shadow(RptScene *S, bool stats, uint32_t *cb) {
   k_shadow<MODE, STATS><<<S->grid[K_SHADOW], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc, w.work + 3)
   if (S->trav_mode == TRAV_SMALL) {
     if (stats) RPT_SHADOW_LAUNCH(TRAV_SMALL, true); else RPT_SHADOW_LAUNCH(TRAV_SMALL, false);
+  } else if (S->trav_mode == TRAV_BVH_REFILL) {
+    if (stats) RPT_SHADOW_LAUNCH(TRAV_BVH_REFILL, true); else RPT_SHADOW_LAUNCH(TRAV_BVH_REFILL, false);
   } else {
     if (stats) RPT_SHADOW_LAUNCH(TRAV_BVH, true); else RPT_SHADOW_LAUNCH(TRAV_BVH, false);
   }
@@ -2580,6 +2773,10 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   {
     const char *e = std::getenv("RPT_TMA_TILES");
     if (e && e[0] == '1' && S->trav_mode == TRAV_BVH) S->trav_mode = TRAV_BVH_TMA;
+    // Lane refill pays where ray lengths vary widely: two-level scenes (a BLAS below the TLAS). RPT_REFILL=0 / 1 overrides.
+    const char *r = std::getenv("RPT_REFILL");
+    const bool want = r ? r[0] == '1' : needed_blas_depth > 0;
+    if (want && S->trav_mode == TRAV_BVH) S->trav_mode = TRAV_BVH_REFILL;
   }
   if (S->stack_smem > 48 * 1024) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -2592,11 +2789,20 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     cudaFuncSetAttribute(k_trace<TRAV_BVH_TMA, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     cudaFuncSetAttribute(k_shadow<TRAV_BVH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     cudaFuncSetAttribute(k_shadow<TRAV_BVH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_REFILL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_REFILL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_REFILL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_REFILL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_shadow<TRAV_BVH_REFILL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_shadow<TRAV_BVH_REFILL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     cudaFuncSetAttribute(k_trace_rays<TRAV_BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   }
   if (S->trav_mode == TRAV_SMALL) {
     S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_SMALL, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
     S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_SMALL, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+  } else if (S->trav_mode == TRAV_BVH_REFILL) {
+    S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH_REFILL, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+    S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH_REFILL, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
   } else if (S->trav_mode == TRAV_BVH_TMA) {
     S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH_TMA, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
     S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH, false>, TRACE_THREADS, S->stack_smem, S->num_sms);

@@ -115,12 +115,25 @@ class CudaRenderer:
     def __init__(self, device: int = 0, num_lambda: int = 1024, seed: int = 0):
         self.device, self.num_lambda, self.seed = device, num_lambda, seed
         self.lib = ffi.load_library()
+        self._flat_cache: Dict[tuple, tuple] = {}
+
+    def flatten(self, world: W.World, wavelength_bounds: Tuple[float, float]) -> ffi.FlatScene:
+        """World -> RptSceneDesc arrays (the shim's flatten.rs). The flattening of an unchanged World is reused: a frame loop
+        over the same scene re-uploads it every frame (rpt_scene_create) but does not re-sample its curves on the host."""
+        key = (id(world), float(wavelength_bounds[0]), float(wavelength_bounds[1]), self.num_lambda)
+        hit = self._flat_cache.get(key)
+        if hit is None or hit[0] is not world:
+            if len(self._flat_cache) >= 8:
+                self._flat_cache.clear()
+            hit = (world, ffi.FlatScene(world, wavelength_bounds[0], wavelength_bounds[1], self.num_lambda))
+            self._flat_cache[key] = hit
+        return hit[1]
 
     def supported_integrators(self) -> List[str]:
         return ["PT"]
 
     def make_scene(self, world: W.World, wavelength_bounds: Tuple[float, float]) -> ffi.Scene:
-        flat = ffi.FlatScene(world, wavelength_bounds[0], wavelength_bounds[1], self.num_lambda)
+        flat = self.flatten(world, wavelength_bounds)
         scene = ffi.Scene(self.lib, flat, self.device)
         env = world.environment
         if env.kind == 2 and env.imap_row_pdf is None and env.imap_request is not None:
@@ -135,7 +148,7 @@ class CudaRenderer:
     def make_multi_scene(self, world: W.World, wavelength_bounds: Tuple[float, float], devices) -> "ffi.MultiScene":
         """`RendererType::Cuda { devices }` of the shim: one replica per device + the in-library spp split and film exchange
         (rpt_multi_*); the importance map of an Unbaked HDR environment is baked on every device."""
-        flat = ffi.FlatScene(world, wavelength_bounds[0], wavelength_bounds[1], self.num_lambda)
+        flat = self.flatten(world, wavelength_bounds)
         ms = ffi.MultiScene(self.lib, flat, devices)
         env = world.environment
         if env.kind == 2 and env.imap_row_pdf is None and env.imap_request is not None:
