@@ -96,6 +96,11 @@ struct DevScene {
   const uint32_t *light_geom;
   const float *light_geom_box;  // 6 floats (world min, max) per entry: the box the reference's BVH gates the shape with
   const RptMaterial *materials;
+  // Per material: (curve LUT id as bits, texel) when its texture stack is exactly one Texture1 of one texel (every
+  // `lambertian_*` of data/lib_materials.toml is: single_pixel.png x a reflectance curve), else (-1, 0). Lets the shade
+  // kernel skip four dependent loads (stack -> texture ids -> texture record -> texel) on its critical path; the value is
+  // the one texstack_eval returns (0 + curve * texel).
+  const float2 *mat_fast;
   const float *curve_lut;
   const float *cie_lut;
   uint32_t num_lambda;
@@ -1157,6 +1162,11 @@ __device__ __forceinline__ GgxParams ggx_params(const DevScene &S, const RptMate
 __device__ __forceinline__ float diffuse_albedo(const DevScene &S, const RptMaterial &m, float lambda, float u, float v) {
   if (m.type == RPT_MATERIAL_LAMBERTIAN) return fminf(texstack_eval(S, m.texstack, lambda, u, v), 1.0f);
   return clampf(curve_eval(S, m.curve_a, lambda), 0.0f, 1.0f);
+}
+__device__ __forceinline__ float diffuse_albedo_fast(const DevScene &S, const RptMaterial &m, float2 fast, float lambda, float u, float v) {
+  const int32_t c = __float_as_int(fast.x);
+  if (m.type == RPT_MATERIAL_LAMBERTIAN && c >= 0) return fminf(0.0f + curve_eval(S, c, lambda) * fast.y, 1.0f);
+  return diffuse_albedo(S, m, lambda, u, v);
 }
 // MaterialEnum::emission (diffuse_light.rs:123-133, sharp_light.rs:138-150,202-204); 0 for non-lights.
 __device__ __forceinline__ float material_emission(const DevScene &S, const RptMaterial &m, float lambda, float3 wi) {

@@ -63,7 +63,8 @@ struct __align__(16) PathRec {
 };
 struct __align__(16) HitRec {
   float t;
-  uint32_t inst, prim, pad;
+  uint32_t inst, prim;
+  uint32_t mat;  // packed MaterialId of the hit (what k_trace classified it by): lets the shade kernel start its material fetch at once
 };
 struct __align__(16) NeeRec {  // NEE hand-over record of the split shade pipeline (layout: see k_shade_vertex)
   float4 r0, r1, r2, r3;
@@ -348,12 +349,12 @@ __device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t m
 // of reading what a separate ray-generation kernel wrote: one 64-byte queue write + read per sample less.
 enum : int { TRAV_BVH = 0, TRAV_BVH_TMA = 1, TRAV_SMALL = 2, TRAV_BVH_REFILL = 3 };  // how the traversal kernels find hits (chosen per scene)
 
-// TRAV_BVH_REFILL: lanes whose ray has finished are re-armed with the next ray of the queue while the other lanes of the
-// warp are still walking ("persistent threads with dynamic fetch", Aila & Laine 2009), once at least REFILL_MIN lanes are
-// idle. Why: on the 10 M-triangle instanced scene every part of the traversal kernels - node loop, leaf code, instance
-// entry - runs at 6.5-7.7 of 32 lanes (ncu source view, profiles/r02_pre_monkeys_*): rays take 5 to 100+ node visits, a warp
-// lives as long as its longest ray, and the lanes of the short rays idle. (Round 1 measured the same idea on the Cornell
-// box, where rays are 7-9 nodes long and there is nothing to recover.)
+// TRAV_BVH_REFILL (opt-in, RPT_REFILL=1): lanes whose ray has finished are re-armed with the next ray of the queue while the
+// other lanes of the warp are still walking ("persistent threads with dynamic fetch", Aila & Laine 2009), once at least
+// REFILL_MIN lanes are idle. Motivation: on the 10 M-triangle instanced scene every part of the traversal kernels - node
+// loop, leaf code, instance entry - runs at 6.5-7.7 of 32 lanes (ncu source view): rays take 5 to 100+ node visits, a warp
+// lives as long as its longest ray, and the lanes of the short rays idle. Outcome (profiles/r02_refill_vs_tile.md): lanes per
+// instruction rise to 9.8-12.8, frame time does not move (213 vs 214 ms); see rpt_scene_create for why it is not the default.
 #ifndef REFILL_MIN
 #define REFILL_MIN 8u
 #endif
@@ -461,8 +462,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
       h.t = th.t;
       h.inst = th.inst;
       h.prim = th.prim;
-      h.pad = 0;
-      hits[i] = h;
+      h.mat = RPT_NONE;
       if (!hit) {
         if (S.env_kind == RPT_ENV_CONSTANT) {
           // The environment vertex of a direction-independent environment is finished here, from the path record that is
@@ -486,7 +486,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
           if ((I.flags & DI_KIND_MASK) == RPT_AGG_MESH) mat = __float_as_uint(__ldg(S.tri_verts + 3 * (size_t)(I.tri_base + th.prim)).w);
         }
         cls = material_class(S, mat);
+        h.mat = mat;
       }
+      hits[i] = h;
     }
     uint32_t k;
     k = chunk_append(counts + Q_MISS, wc_miss, cls == Q_MISS, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
@@ -559,8 +561,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
           h.t = t.out.t;
           h.inst = t.out.inst;
           h.prim = t.out.prim;
-          h.pad = 0;
-          hits[my_i] = h;
+          h.mat = RPT_NONE;
           if (!t.found) {
             if (S.env_kind == RPT_ENV_CONSTANT) {  // as in the tile form below, from the re-read path record
               const float4 *rp = reinterpret_cast<const float4 *>(src + my_i);
@@ -584,7 +585,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
               if ((I.flags & DI_KIND_MASK) == RPT_AGG_MESH) mat = __float_as_uint(__ldg(S.tri_verts + 3 * (size_t)(I.tri_base + t.out.prim)).w);
             }
             cls = material_class(S, mat);
+            h.mat = mat;
           }
+          hits[my_i] = h;
         }
         uint32_t k;
         k = chunk_append(counts + Q_MISS, wc_miss, cls == Q_MISS, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
@@ -996,13 +999,18 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_shade_vertex(DevScene S, R
       lambda = r.r2.w;
       slot = __float_as_uint(r.r3.x);
       float3 o = rec_origin(r);
+      // the material id travels in the hit record (k_trace classified the vertex by it): its table entries are fetched
+      // here, next to the instance / triangle loads of reconstruct_hit, instead of after them
+      const uint32_t hit_mat = __float_as_uint(hraw.w);
+      const RptMaterial m = S.materials[RPT_MAT_INDEX(hit_mat)];
+      const float2 m_fast = __ldg(S.mat_fast + RPT_MAT_INDEX(hit_mat));
       SurfaceHit sh;
       reconstruct_hit(S, o, d, th, sh);
+      sh.material = hit_mat;  // (the same id reconstruct_hit derives: instance override, else the triangle's)
       hp = sh.p;
       hn = sh.n;
       Frame frame = frame_from_normal(sh.n);
       float3 wi = normalized(to_local(frame, -d));  // integrator/utils.rs:175-176
-      const RptMaterial m = S.materials[RPT_MAT_INDEX(sh.material)];
       const uint32_t pixel = slot % R.wh, sample = R.sample_base + slot / R.wh;
       RptRand4 s = rpt_philox(R.seed, pixel, sample, rpt_block_bsdf(bounce, L));
 
@@ -1015,7 +1023,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_shade_vertex(DevScene S, R
         pdf = b.pdf;
         extra = make_float4(gp.eta_inner, gp.eta_outer, gp.kappa, __uint_as_float(RPT_MAT_INDEX(sh.material)));
       } else {
-        float albedo = diffuse_albedo(S, m, lambda, sh.u, sh.v);
+        float albedo = diffuse_albedo_fast(S, m, m_fast, lambda, sh.u, sh.v);
         wo = random_cosine_direction(s.x, s.y) * signumf(wi.z);
         f = albedo / RPT_PI;
         pdf = fabsf(wo.z) / RPT_PI;
@@ -1777,7 +1785,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32
       h.t = th.t;
       h.inst = th.inst;
       h.prim = th.prim;
-      h.pad = 0;
+      h.mat = RPT_NONE;
       hits[i] = h;
     }
   }
@@ -1896,6 +1904,11 @@ struct RptScene {
 
 namespace {
 
+float __int_as_float_host(int32_t v) {
+  float f;
+  std::memcpy(&f, &v, 4);
+  return f;
+}
 void to3x4(const float *m16, float4 *out) {
   for (int r = 0; r < 3; ++r) out[r] = make_float4(m16[4 * r], m16[4 * r + 1], m16[4 * r + 2], m16[4 * r + 3]);
 }
@@ -2198,7 +2211,8 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
       const WaveCache &c = g_wave_cache[S->device];
       if (c.valid) held += c.slots * kPathSlotBytes + c.shadow * kShadowSlotBytes + c.acc * sizeof(float);
     }
-    size_t budget = std::min<size_t>((size_t)((free_b + held) * 0.5), (size_t)32 << 30);
+    // half of what is free, at most 96 GB: a 4K x 16 spp frame (133 M paths, ~45 GB of queues) is still one wave on a 180 GB B200
+    size_t budget = std::min<size_t>((size_t)((free_b + held) * 0.5), (size_t)96 << 30);
     // the queue capacities are affine in the slot count: fixed part (end-of-kernel chunk tails) + per-slot part
     size_t fixed = wave_bytes(S, 0, P->light_samples);
     size_t per_1k = wave_bytes(S, 1024, P->light_samples) - fixed;
@@ -2722,6 +2736,18 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     texs[t].height = T.height;
     std::memcpy(texs[t].curves, T.curves, sizeof(T.curves));
   }
+  {
+    std::vector<float2> mat_fast(d->num_materials, make_float2(__int_as_float_host(-1), 0.0f));
+    for (uint32_t i = 0; i < d->num_materials; ++i) {
+      const RptMaterial &M = d->materials[i];
+      if (M.type != RPT_MATERIAL_LAMBERTIAN || M.texstack < 0 || (uint32_t)M.texstack >= d->num_texstacks) continue;
+      const RptTexStack &st = d->texstacks[M.texstack];
+      if (st.count != 1) continue;
+      const RptTexture &T = d->textures[d->texstack_textures[st.first]];
+      if (T.channels == 1 && T.width == 1 && T.height == 1 && T.curves[0] >= 0) mat_fast[i] = make_float2(__int_as_float_host(T.curves[0]), T.texels[0]);
+    }
+    rc |= B.upload(mat_fast.data(), mat_fast.size(), &D.mat_fast);
+  }
   rc |= B.upload(texs.data(), texs.size(), &D.textures);
   rc |= B.upload(d->texstack_textures, d->num_texstack_textures, &D.stack_tex);
   rc |= B.upload(d->texstacks, d->num_texstacks, &D.stacks);
@@ -2773,10 +2799,12 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   {
     const char *e = std::getenv("RPT_TMA_TILES");
     if (e && e[0] == '1' && S->trav_mode == TRAV_BVH) S->trav_mode = TRAV_BVH_TMA;
-    // Lane refill pays where ray lengths vary widely: two-level scenes (a BLAS below the TLAS). RPT_REFILL=0 / 1 overrides.
+    // Lane refill is opt-in (RPT_REFILL=1). Measured (profiles/r02_refill_vs_tile.md): on the instanced 10 M-triangle scene
+    // it lifts the traversal kernels from 6.5 to 9.8 lanes per instruction, but pays for it with re-read records, a lower
+    // issue rate (long-scoreboard stalls 3.5 -> 4.2 per issue) and the per-step bookkeeping: 213 vs 214 ms per frame. On the
+    // Cornell box (short rays) it loses 38 %, on the gem scene 12 %.
     const char *r = std::getenv("RPT_REFILL");
-    const bool want = r ? r[0] == '1' : needed_blas_depth > 0;
-    if (want && S->trav_mode == TRAV_BVH) S->trav_mode = TRAV_BVH_REFILL;
+    if (r && r[0] == '1' && S->trav_mode == TRAV_BVH) S->trav_mode = TRAV_BVH_REFILL;
   }
   if (S->stack_smem > 48 * 1024) {
     std::lock_guard<std::mutex> lk(g_cache_mu);

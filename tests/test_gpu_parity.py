@@ -143,6 +143,12 @@ def test_furnace_exact(scenes):
     assert abs(corner_g - corner_o) / corner_o < 1e-3
     centre_g = float(fg[56:72, 56:72, 1].mean())
     print(f"furnace_exact: mean Y gpu {yg:.6f} oracle {yo:.6f}; centre/corner = {centre_g / corner_g:.4f} (1.0 = energy conserving)")
+    # BASELINE.json check (b) says "returns 1.0 within 1e-3"; the REFERENCE's estimator returns 1.0723 at the centre of this
+    # sphere (quadrature + derivation: tests/test_oracle_golden.py::furnace_expectation, BASELINE.md "Furnace"), and so must we
+    from test_oracle_golden import furnace_expectation
+
+    sigma = 1.2 / np.sqrt(256 * 256) + 1.2 / np.sqrt(64 * 256)
+    assert abs(centre_g / corner_g - furnace_expectation([-1, 0, 0])) < 3 * sigma + 0.005, centre_g / corner_g
 
 
 def test_furnace_shipped(scenes):
@@ -496,8 +502,8 @@ def test_small_scene_mode_equals_bvh(monkeypatch, name):
 
 @pytest.mark.parametrize("name", ["cornell", "gem", "instanced_monkeys", "kitchen_sink", "hdri2", "sun_test"])
 def test_lane_refill_mode_equals_tile_mode(monkeypatch, name):
-    """TRAV_BVH_REFILL (finished lanes are re-armed with the next ray of the queue while the rest of the warp keeps walking;
-    the default for two-level scenes, RPT_REFILL=0 / 1 overrides) answers the same queries as the tile-at-a-time walk:
+    """TRAV_BVH_REFILL (RPT_REFILL=1: finished lanes are re-armed with the next ray of the queue while the rest of the warp
+    keeps walking; opt-in after measurement, profiles/r02_refill_vs_tile.md) answers the same queries as the tile-at-a-time walk:
     same hit ids, same counters, same film up to the order of the energy atomics."""
     world, st, flat = parity.load_scene(name, 192, 108, 4)
     monkeypatch.setenv("RPT_REFILL", "0")
