@@ -127,6 +127,7 @@ struct DevScene {
   const uint4 *small_leaves; // per leaf: instance id, mesh-local triangle id, triangle candidate order, instance candidate order
   const float *small_boxes;  // per instance leaf (index k - small_ntri) 6 floats: the box the reference's BVH gates the shape with
   float3 world_center; // centre of the scene bounds (ray binning only)
+  float3 world_min, world_inv_extent;  // scene bounds for the NEE origin-cell grid (ray binning only)
   float p_env;         // effective env sampling probability (1 when there are no lights)
   float world_radius;  // World.radius (world/mod.rs:69-72); informational
 };

@@ -189,7 +189,7 @@ __device__ __forceinline__ uint32_t chunk_append(uint32_t *counter, WarpChunk &w
 // kernels run 30 of 32 lanes on the coherent first bounce but 11-13 on unsorted later bounces.
 #define NBINS 8u
 #define QCHUNK_BINNED 128u
-template <class Mark>
+template <uint32_t CH = QCHUNK_BINNED, class Mark>
 __device__ __forceinline__ uint32_t chunk_append_binned(uint32_t *counter, WarpChunk *st, bool pred, uint32_t bin, Mark mark) {
   uint32_t active = __ballot_sync(0xFFFFFFFFu, pred);
   uint32_t idx = RPT_NONE;
@@ -200,9 +200,9 @@ __device__ __forceinline__ uint32_t chunk_append_binned(uint32_t *counter, WarpC
     uint32_t first = 0;
     if (lane == leader) {
       WarpChunk wc = st[bin];
-      if (wc.used + cnt > QCHUNK_BINNED) {
-        for (uint32_t e = wc.used; e < QCHUNK_BINNED; ++e) mark(wc.base + e);  // < 32 entries unless the chunk was never used
-        wc.base = atomicAdd(counter, QCHUNK_BINNED);
+      if (wc.used + cnt > CH) {
+        for (uint32_t e = wc.used; e < CH; ++e) mark(wc.base + e);  // < 32 entries unless the chunk was never used
+        wc.base = atomicAdd(counter, CH);
         wc.used = 0;
       }
       first = wc.base + wc.used;
@@ -214,12 +214,12 @@ __device__ __forceinline__ uint32_t chunk_append_binned(uint32_t *counter, WarpC
   __syncwarp();
   return idx;
 }
-template <class Mark>
+template <uint32_t CH = QCHUNK_BINNED, class Mark>
 __device__ __forceinline__ void chunk_pad_binned(const WarpChunk *st, uint32_t nbins, Mark mark) {
   uint32_t lane = threadIdx.x & 31u;
   for (uint32_t b = 0; b < nbins; ++b) {
     WarpChunk wc = st[b];
-    for (uint32_t e = wc.used + lane; e < QCHUNK_BINNED; e += 32u) mark(wc.base + e);
+    for (uint32_t e = wc.used + lane; e < CH; e += 32u) mark(wc.base + e);
   }
 }
 
@@ -1099,19 +1099,29 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_shade_vertex(DevScene S, R
 // NEE sample generation for the vertices k_shade_vertex handed over (estimate_direct_illumination_with_loop, pt.rs:333-393;
 // light samples pt.rs:146-219, environment samples pt.rs:224-331). One vertex per lane, L samples each; every sample that
 // can contribute becomes a shadow ray, appended binned by origin cell (see k_shade_surface).
+// NEE rays are binned by the cell of the scene bounds their origin lies in (NEE_GRID^3 cells), one queue chunk of NEE_CHUNK
+// rays per (warp, cell): a consumer warp of k_shadow then traces rays that start close together and (light samples) head for
+// the same light.
+#ifndef NEE_GRID
+#define NEE_GRID 2u
+#endif
+#ifndef NEE_CHUNK
+#define NEE_CHUNK 128u
+#endif
+#define NEE_BINS (NEE_GRID * NEE_GRID * NEE_GRID)
 template <uint32_t CLASS>
 __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx R, uint32_t bounce, const NeeRec *__restrict__ nee,
                                                          uint32_t *__restrict__ counts, float4 *__restrict__ sh_a, float4 *__restrict__ sh_b,
                                                          uint32_t *__restrict__ sh_c) {
-  __shared__ WarpChunk s_chunks[SHADE_THREADS / 32][NBINS];
+  __shared__ WarpChunk s_chunks[SHADE_THREADS / 32][NEE_BINS];
   WarpChunk *st_shadow = s_chunks[threadIdx.x >> 5];
-  if ((threadIdx.x & 31u) < NBINS) st_shadow[threadIdx.x & 31u] = WarpChunk{0u, QCHUNK_BINNED};
+  for (uint32_t b = threadIdx.x & 31u; b < NEE_BINS; b += 32u) st_shadow[b] = WarpChunk{0u, NEE_CHUNK};
   __syncwarp();
   const uint32_t n = counts[CLASS == Q_DIFFUSE ? Q_NEE_DIFFUSE : Q_NEE_GGX];
   const uint32_t L = R.light_samples;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_tiles = (n + 31u) >> 5;
-  const uint32_t nbins = n >= BIN_MIN_ITEMS ? NBINS : 1u;  // small queues: binning would only scatter a few rays over many chunks
+  const uint32_t nbins = n >= BIN_MIN_ITEMS ? NEE_BINS : 1u;  // small queues: binning would only scatter a few rays over many chunks
   uint32_t n_shadow = 0, n_sh_ref = 0;
   auto mark_shadow = [&](uint32_t e) { sh_c[e] = RPT_NONE; };
   const float inv_l = 1.0f / (float)L;
@@ -1204,8 +1214,15 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
           }
         }
       }
-      uint32_t bin_sh = nbins > 1 ? ((a.x < S.world_center.x) | ((a.y < S.world_center.y) << 1) | ((a.z < S.world_center.z) << 2)) : 0u;  // origin cell
-      uint32_t q = chunk_append_binned(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow);
+      uint32_t bin_sh = 0u;
+      if (nbins > 1) {  // origin cell
+        const float g = (float)NEE_GRID;
+        uint32_t cx = (uint32_t)fminf(fmaxf((a.x - S.world_min.x) * S.world_inv_extent.x * g, 0.0f), g - 1.0f);
+        uint32_t cy = (uint32_t)fminf(fmaxf((a.y - S.world_min.y) * S.world_inv_extent.y * g, 0.0f), g - 1.0f);
+        uint32_t cz = (uint32_t)fminf(fmaxf((a.z - S.world_min.z) * S.world_inv_extent.z * g, 0.0f), g - 1.0f);
+        bin_sh = (cz * NEE_GRID + cy) * NEE_GRID + cx;
+      }
+      uint32_t q = chunk_append_binned<NEE_CHUNK>(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow);
       if (has) {
         sh_a[q] = a;
         sh_b[q] = b4;
@@ -1214,7 +1231,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
       n_shadow += has;
     }
   }
-  chunk_pad_binned(st_shadow, NBINS, mark_shadow);
+  chunk_pad_binned<NEE_CHUNK>(st_shadow, NEE_BINS, mark_shadow);
   flush_count(n_shadow, counts + N_SHADOW);
   flush_count(n_sh_ref, counts + Q_SHADOW_REF);  // reference-definition shadow-ray counter (pt.rs:176,252)
 }
@@ -2002,8 +2019,10 @@ size_t path_queue_cap(const RptScene *S, size_t valid) {  // next-path queue, cl
 }
 size_t shadow_queue_cap(const RptScene *S, size_t valid) {
   size_t shade_warps = ((size_t)std::max(S->grid[K_SHADE_DIFFUSE], S->grid[K_NEE_DIFFUSE]) + (size_t)std::max(S->grid[K_SHADE_GGX], S->grid[K_NEE_GGX])) * (SHADE_THREADS / 32);
-  size_t tail = shade_warps * NBINS * QCHUNK_BINNED;
-  return valid + (valid * 31 + (QCHUNK_BINNED - 31) - 1) / (QCHUNK_BINNED - 31) + tail + QCHUNK_BINNED;
+  const size_t bins = std::max<size_t>(NBINS, NEE_BINS), chunk = std::min<size_t>(QCHUNK_BINNED, NEE_CHUNK);
+  size_t tail = shade_warps * std::max<size_t>((size_t)NBINS * QCHUNK_BINNED, (size_t)NEE_BINS * NEE_CHUNK);
+  (void)bins;
+  return valid + (valid * 31 + (chunk - 31) - 1) / (chunk - 31) + tail + QCHUNK_BINNED;
 }
 constexpr size_t kPathSlotBytes = 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t) + 2 * sizeof(NeeRec);
 constexpr size_t kShadowSlotBytes = 2 * sizeof(float4) + sizeof(uint32_t);
@@ -2780,6 +2799,8 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   float span[3] = {world.mx[0] - world.mn[0], world.mx[1] - world.mn[1], world.mx[2] - world.mn[2]};
   D.world_radius = std::sqrt(span[0] * span[0] + span[1] * span[1] + span[2] * span[2]) / 2.0f;
   D.world_center = make_float3(world.mn[0] + span[0] / 2.0f, world.mn[1] + span[1] / 2.0f, world.mn[2] + span[2] / 2.0f);
+  D.world_min = make_float3(world.mn[0], world.mn[1], world.mn[2]);
+  D.world_inv_extent = make_float3(span[0] > 0 ? 1.0f / span[0] : 0.0f, span[1] > 0 ? 1.0f / span[1] : 0.0f, span[2] > 0 ? 1.0f / span[2] : 0.0f);
   S->cameras.assign(d->cameras, d->cameras + d->num_cameras);
 
   S->stats.instances = d->num_instances;

@@ -120,7 +120,11 @@ class CudaRenderer:
     def flatten(self, world: W.World, wavelength_bounds: Tuple[float, float]) -> ffi.FlatScene:
         """World -> RptSceneDesc arrays (the shim's flatten.rs). The flattening of an unchanged World is reused: a frame loop
         over the same scene re-uploads it every frame (rpt_scene_create) but does not re-sample its curves on the host."""
-        key = (id(world), float(wavelength_bounds[0]), float(wavelength_bounds[1]), self.num_lambda)
+        # the key covers what this package itself replaces on a live World (cameras re-aspected per render setting, importance
+        # map tables baked / requested); anything else is treated as immutable once flattened
+        env = world.environment
+        key = (id(world), float(wavelength_bounds[0]), float(wavelength_bounds[1]), self.num_lambda, tuple(id(c) for c in world.cameras),
+               id(env.imap_row_pdf), id(env.imap_request), env.kind, len(world.instances), len(world.materials), len(world.curves))
         hit = self._flat_cache.get(key)
         if hit is None or hit[0] is not world:
             if len(self._flat_cache) >= 8:

@@ -20,7 +20,7 @@ units = {r[ix["Metric Name"]]: r[ix["Metric Unit"]] for r in rows}
 def short(n):
     m = re.search(r"(k_[a-z_]+)(<[^>]*>)?", n)
     base, t = m.group(1), m.group(2) or ""
-    if base == "k_shade_surface":
+    if base in ("k_shade_surface", "k_shade_vertex", "k_nee"):
         return base + ("<diffuse>" if "2" in t else "<ggx>")
     return base
 
