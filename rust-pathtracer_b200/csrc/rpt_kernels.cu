@@ -929,8 +929,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
 //   r2 = wi (local, towards the previous vertex).xyz, slot bits
 //   r3 = diffuse: albedo, -, -, -            ggx: eta_inner, eta_outer, kappa, material index bits
 // The tangent frame is rebuilt from the normal (frame_from_normal is a pure function of it), pixel / sample from the slot.
+#ifndef VERTEX_MIN_BLOCKS
+#define VERTEX_MIN_BLOCKS 8  // 64 registers, 50 % occupancy
+#endif
 template <uint32_t CLASS>
-__global__ void __launch_bounds__(SHADE_THREADS, 8) k_shade_vertex(DevScene S, RenderCtx R, uint32_t bounce, const PathRec *__restrict__ paths,
+__global__ void __launch_bounds__(SHADE_THREADS, VERTEX_MIN_BLOCKS) k_shade_vertex(DevScene S, RenderCtx R, uint32_t bounce, const PathRec *__restrict__ paths,
                                                                   const HitRec *__restrict__ hits, const uint32_t *__restrict__ queue,
                                                                   uint32_t *__restrict__ counts, uint32_t *__restrict__ next_counts,
                                                                   PathRec *__restrict__ out, NeeRec *__restrict__ nee, float *__restrict__ acc) {
