@@ -1895,6 +1895,8 @@ struct RptScene {
   std::vector<RptCamera> cameras;
   RptSceneStats stats{};
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // the second half-wave's stream (render_waves), created on first use
+  cudaEvent_t ev_join = nullptr;   // fork / join between the two
   // wave buffers (grown on demand, reused across calls)
   WaveBuffers wave{};
   size_t wave_slots = 0, wave_shadow = 0, wave_acc = 0;  // capacities: path-queue entries, shadow entries, energy slots
@@ -1993,6 +1995,8 @@ struct WaveCache {
   // host for 20-70 ms in one frame out of five (measured, tools/e2e_probe.py), with the device time unchanged
   cudaStream_t stream = nullptr;
   std::vector<cudaEvent_t> events;
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_join = nullptr;
 };
 WaveCache g_wave_cache[64];
 
@@ -2027,10 +2031,14 @@ size_t shadow_queue_cap(const RptScene *S, size_t valid) {
   (void)bins;
   return valid + (valid * 31 + (chunk - 31) - 1) / (chunk - 31) + tail + QCHUNK_BINNED;
 }
+// The wave buffers are provisioned for TWO half-waves (render_waves runs the two halves of a wave on two streams so that the
+// ragged tail of one half's launches overlaps the other half's work): each queue holds twice the capacity of half the slots.
+size_t wave_path_cap(const RptScene *S, size_t slots) { return 2 * path_queue_cap(S, (slots + 1) / 2); }
+size_t wave_shadow_cap(const RptScene *S, size_t shadow_valid) { return 2 * shadow_queue_cap(S, (shadow_valid + 1) / 2); }
 constexpr size_t kPathSlotBytes = 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t) + 2 * sizeof(NeeRec);
 constexpr size_t kShadowSlotBytes = 2 * sizeof(float4) + sizeof(uint32_t);
 size_t wave_bytes(const RptScene *S, size_t slots, uint32_t light_samples) {
-  return path_queue_cap(S, slots) * kPathSlotBytes + shadow_queue_cap(S, slots * light_samples) * kShadowSlotBytes + slots * sizeof(float);
+  return wave_path_cap(S, slots) * kPathSlotBytes + wave_shadow_cap(S, slots * light_samples) * kShadowSlotBytes + slots * sizeof(float);
 }
 
 // Called at scene destruction: park the buffers in the device's cache (keeping the larger set).
@@ -2055,7 +2063,7 @@ void park_wave(RptScene *S) {
 
 // slots = camera samples in a wave; shadow_valid = NEE rays a bounce can emit; bounces = per-bounce counter rows needed
 int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid, size_t bounces) {
-  size_t pcap = path_queue_cap(S, slots), scap = shadow_queue_cap(S, shadow_valid);
+  size_t pcap = wave_path_cap(S, slots), scap = wave_shadow_cap(S, shadow_valid);
   if (pcap <= S->wave_slots && scap <= S->wave_shadow && slots <= S->wave_acc && bounces <= S->counts_cap) return 0;
   free_wave(S);
   if (S->device >= 0 && S->device < 64) {
@@ -2092,9 +2100,9 @@ int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid, size_t bounces) 
   CUDA_TRY(cudaMalloc(&w.sh_b, scap * sizeof(float4)));
   CUDA_TRY(cudaMalloc(&w.sh_c, scap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&w.acc, slots * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&w.counts, (ccap + 1) * Q_COUNT * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&w.work, 6 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(w.work, 0, 6 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&w.counts, 2 * (ccap + 1) * Q_COUNT * sizeof(uint32_t)));  // one block of rows per half-wave
+  CUDA_TRY(cudaMalloc(&w.work, 12 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(w.work, 0, 12 * sizeof(unsigned long long)));
   S->wave_slots = pcap;
   S->wave_shadow = scap;
   S->wave_acc = slots;
@@ -2157,11 +2165,10 @@ RenderCtx make_ctx(const RptScene *S, const RptRenderParams *P) {
 
 // ---- kernel dispatch over the (traversal mode, statistics) template parameters
 template <bool RAYGEN>
-void launch_trace(RptScene *S, bool stats, const PathRec *in, uint32_t *cb, const RenderCtx &R, PathRec *paths_out) {
-  WaveBuffers &w = S->wave;
-#define RPT_TRACE_LAUNCH(MODE, STATS)                                                                                                         \
-  k_trace<MODE, RAYGEN, STATS><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, \
-                                                                                               w.work, w.acc, R, paths_out)
+void launch_trace(RptScene *S, const WaveBuffers &w, cudaStream_t st, bool stats, const PathRec *in, uint32_t *cb, const RenderCtx &R, PathRec *paths_out) {
+#define RPT_TRACE_LAUNCH(MODE, STATS)                                                                                                 \
+  k_trace<MODE, RAYGEN, STATS><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, st>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, \
+                                                                                       w.work, w.acc, R, paths_out)
   if (S->trav_mode == TRAV_SMALL) {
     if (stats) RPT_TRACE_LAUNCH(TRAV_SMALL, true); else RPT_TRACE_LAUNCH(TRAV_SMALL, false);
   } else if (S->trav_mode == TRAV_BVH_REFILL) {
@@ -2171,18 +2178,16 @@ void launch_trace(RptScene *S, bool stats, const PathRec *in, uint32_t *cb, cons
   }
 #undef RPT_TRACE_LAUNCH
 }
-void launch_trace_tma(RptScene *S, bool stats, const PathRec *in, uint32_t *cb) {
-  WaveBuffers &w = S->wave;
+void launch_trace_tma(RptScene *S, const WaveBuffers &w, cudaStream_t st, bool stats, const PathRec *in, uint32_t *cb) {
   RenderCtx R{};
   if (stats)
-    k_trace<TRAV_BVH_TMA, false, true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc, R, nullptr);
+    k_trace<TRAV_BVH_TMA, false, true><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, st>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc, R, nullptr);
   else
-    k_trace<TRAV_BVH_TMA, false, false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc, R, nullptr);
+    k_trace<TRAV_BVH_TMA, false, false><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, st>>>(S->dev, in, w.hits, w.q_miss, w.q_diffuse, w.q_ggx, cb, w.work, w.acc, R, nullptr);
 }
-void launch_shadow(RptScene *S, bool stats, uint32_t *cb) {
-  WaveBuffers &w = S->wave;
+void launch_shadow(RptScene *S, const WaveBuffers &w, cudaStream_t st, bool stats, uint32_t *cb) {
 #define RPT_SHADOW_LAUNCH(MODE, STATS) \
-  k_shadow<MODE, STATS><<<S->grid[K_SHADOW], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc, w.work + 3)
+  k_shadow<MODE, STATS><<<S->grid[K_SHADOW], TRACE_THREADS, S->stack_smem, st>>>(S->dev, w.sh_a, w.sh_b, w.sh_c, cb, w.acc, w.work + 3)
   if (S->trav_mode == TRAV_SMALL) {
     if (stats) RPT_SHADOW_LAUNCH(TRAV_SMALL, true); else RPT_SHADOW_LAUNCH(TRAV_SMALL, false);
   } else if (S->trav_mode == TRAV_BVH_REFILL) {
@@ -2221,8 +2226,8 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   // scene already holds fit the whole job, skip the (slow) memory query: a steady-state frame loop allocates nothing.
   uint32_t spp_chunk;
   size_t want_slots = wh * (size_t)std::max<uint32_t>(P->spp, 1);
-  if (want_slots < ((size_t)1 << 30) && path_queue_cap(S, want_slots) <= S->wave_slots &&
-      shadow_queue_cap(S, want_slots * P->light_samples) <= S->wave_shadow && want_slots <= S->wave_acc && max_bounces <= S->counts_cap) {
+  if (want_slots < ((size_t)1 << 30) && wave_path_cap(S, want_slots) <= S->wave_slots &&
+      wave_shadow_cap(S, want_slots * P->light_samples) <= S->wave_shadow && want_slots <= S->wave_acc && max_bounces <= S->counts_cap) {
     spp_chunk = std::max<uint32_t>(P->spp, 1);
   } else {
     size_t free_b = 0, total_b = 0;
@@ -2255,120 +2260,195 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   std::memset(S->kernel_ms, 0, sizeof(S->kernel_ms));
   std::memset(S->kernel_launches, 0, sizeof(S->kernel_launches));
   Launcher T{S, (P->flags & RPT_FLAG_KERNEL_TIMES) != 0};
-  RenderCtx R = make_ctx(S, P);
-  WaveBuffers &w = S->wave;
-  const size_t n_counts = ((size_t)max_bounces + 1) * Q_COUNT;
-  std::vector<uint32_t> h_counts(n_counts);
+  const RenderCtx R0 = make_ctx(S, P);
+  const size_t rows = S->counts_cap + 1;                      // counter rows of one half-wave block
+  const size_t n_counts = ((size_t)max_bounces + 1) * Q_COUNT;  // ... of which this job uses the first max_bounces + 1
+  std::vector<uint32_t> h_counts(2 * rows * Q_COUNT);
   RptCounters C{};
   size_t film_smem = 3 * (size_t)S->dev.num_lambda * sizeof(float);
+  // Two half-waves on two streams: every kernel of the pipeline is a persistent grid that fills the machine, and every
+  // launch ends in a ragged tail where SMs run dry one by one while the last tiles finish (a 16 spp Cornell frame costs
+  // 20.7 ms, one eighth of a 128 spp frame 18.8 ms: ~2 ms of tails and fixed costs per 49 launches). With the wave cut in
+  // two independent halves (disjoint sample ranges, disjoint halves of every queue) on two streams, the CTAs of the other
+  // half's pending launch move in as soon as a tail frees SMs. Off when per-kernel timing is on (the spans would overlap),
+  // for 1-spp waves, and with RPT_NO_OVERLAP=1.
+  const char *no_ov = std::getenv("RPT_NO_OVERLAP");
+  const bool overlap_ok = !T.timed && !(no_ov && no_ov[0] == '1');
+  if (overlap_ok && !S->stream2) {
+    {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      WaveCache &sc = g_wave_cache[S->device & 63];
+      if (sc.stream2) {
+        S->stream2 = sc.stream2;
+        S->ev_join = sc.ev_join;
+        sc.stream2 = nullptr;
+        sc.ev_join = nullptr;
+      }
+    }
+    if (!S->stream2) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&S->stream2, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
+    }
+  }
+  auto part_view = [&](int k, size_t slot_off) {
+    WaveBuffers v = S->wave;
+    const size_t poff = (size_t)k * (S->wave_slots / 2), soff = (size_t)k * (S->wave_shadow / 2);
+    v.paths[0] += poff; v.paths[1] += poff; v.hits += poff;
+    v.q_miss += poff; v.q_diffuse += poff; v.q_ggx += poff; v.nee_d += poff; v.nee_g += poff;
+    v.sh_a += soff; v.sh_b += soff; v.sh_c += soff;
+    v.acc += slot_off;
+    v.counts += (size_t)k * rows * Q_COUNT;
+    v.work += (size_t)k * 6;
+    return v;
+  };
 
-  if (stats) CUDA_TRY(cudaMemsetAsync(w.work, 0, 6 * sizeof(unsigned long long), S->stream));
+  if (stats) CUDA_TRY(cudaMemsetAsync(S->wave.work, 0, 12 * sizeof(unsigned long long), S->stream));
   size_t ev_first = S->ev_used;
   cudaEventRecord(T.next_event(), S->stream);
   for (uint32_t done = 0; done < P->spp; done += spp_chunk) {
-    uint32_t chunk = std::min(spp_chunk, P->spp - done);
-    R.n_slots = (uint32_t)(wh * chunk);
-    R.sample_base = P->spp_offset + done;
-    CUDA_TRY(cudaMemsetAsync(w.counts, 0, n_counts * sizeof(uint32_t), S->stream));
-    CUDA_TRY(cudaMemsetAsync(w.acc, 0, (size_t)R.n_slots * sizeof(float), S->stream));
-    const bool tma = S->trav_mode == TRAV_BVH_TMA;
-    if (tma) {  // (the other modes generate the camera vertices inside bounce 0's k_trace)
-      T.begin(K_RAYGEN);
-      k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
-      T.end();
+    const uint32_t chunk = std::min(spp_chunk, P->spp - done);
+    const int parts = (overlap_ok && chunk >= 2) ? 2 : 1;
+    struct Part {
+      WaveBuffers w;
+      RenderCtx R;
+      cudaStream_t st;
+      uint32_t bounces_run;
+      bool dead;
+    } part[2];
+    for (int k = 0; k < parts; ++k) {
+      const uint32_t spp_a = parts == 2 ? (chunk + 1) / 2 : chunk;
+      const uint32_t spp_k = k == 0 ? spp_a : chunk - spp_a, first = k == 0 ? 0 : spp_a;
+      Part &p = part[k];
+      p.w = part_view(k, wh * (size_t)first);
+      p.R = R0;
+      p.R.n_slots = (uint32_t)(wh * spp_k);
+      p.R.sample_base = P->spp_offset + done + first;
+      p.st = k == 0 ? S->stream : S->stream2;
+      p.bounces_run = 0;
+      p.dead = false;
+      if (k == 1) {  // the second stream starts after what the first has queued so far (film clear, the previous wave's film pass)
+        CUDA_TRY(cudaEventRecord(S->ev_join, S->stream));
+        CUDA_TRY(cudaStreamWaitEvent(S->stream2, S->ev_join, 0));
+      }
+      CUDA_TRY(cudaMemsetAsync(p.w.counts, 0, n_counts * sizeof(uint32_t), p.st));
+      CUDA_TRY(cudaMemsetAsync(p.w.acc, 0, (size_t)p.R.n_slots * sizeof(float), p.st));
     }
-    uint32_t bounces_run = 0;
+    const bool tma = S->trav_mode == TRAV_BVH_TMA;
+    if (tma)  // (the other modes generate the camera vertices inside bounce 0's k_trace)
+      for (int k = 0; k < parts; ++k) {
+        T.begin(K_RAYGEN);
+        k_raygen<<<S->grid[K_RAYGEN], 256, 0, part[k].st>>>(S->dev, part[k].R, part[k].w.paths[0], part[k].w.counts);
+        T.end();
+      }
     for (uint32_t b = 0; b < max_bounces; ++b) {
-      // Long walks (the reference accepts max_bounces up to 65535): once past 16 bounces, look at the path count every 8
-      // bounces and stop launching when the wave has died out (russian roulette empties it long before).
-      if (b >= 16 && (b & 7u) == 0) {
-        uint32_t alive = 0;
-        CUDA_TRY(cudaMemcpyAsync(&alive, w.counts + (size_t)b * Q_COUNT + N_PATHS, sizeof(uint32_t), cudaMemcpyDeviceToHost, S->stream));
-        CUDA_TRY(cudaStreamSynchronize(S->stream));
-        if (alive == 0) break;
-      }
-      bounces_run = b + 1;
-      uint32_t *cb = w.counts + (size_t)b * Q_COUNT, *cn = w.counts + (size_t)(b + 1) * Q_COUNT;
-      PathRec *in = w.paths[b & 1], *out = w.paths[(b + 1) & 1];
-      T.begin(K_TRACE);
-      if (tma)
-        launch_trace_tma(S, stats, in, cb);
-      else if (b == 0)
-        launch_trace<true>(S, stats, nullptr, cb, R, in);
-      else
-        launch_trace<false>(S, stats, in, cb, R, nullptr);
-      T.end();
-      if (S->dev.env_kind != RPT_ENV_CONSTANT) {  // (a Constant environment's vertices are finished inside k_trace)
-        T.begin(K_SHADE_MISS);
-        k_shade_miss<<<S->grid[K_SHADE_MISS], 256, 0, S->stream>>>(S->dev, in, w.q_miss, cb, w.acc);
-        T.end();
-      }
-      if (S->fused_shade) {
-        T.begin(K_SHADE_DIFFUSE);
-        k_shade_surface<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
-        T.end();
-        if (S->has_ggx) {  // (no GGX material in the scene: the class list stays empty, skip its 12 launches per wave)
-          T.begin(K_SHADE_GGX);
-          k_shade_surface<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
-          T.end();
-        }
-      } else {
-        T.begin(K_SHADE_DIFFUSE);
-        k_shade_vertex<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.nee_d, w.acc);
-        T.end();
-        if (S->has_ggx) {
-          T.begin(K_SHADE_GGX);
-          k_shade_vertex<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.nee_g, w.acc);
-          T.end();
-        }
-        if (P->light_samples > 0) {
-          T.begin(K_NEE_DIFFUSE);
-          k_nee<Q_DIFFUSE><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
-          T.end();
-          if (S->has_ggx) {
-            T.begin(K_NEE_GGX);
-            k_nee<Q_GGX><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, S->stream>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
-            T.end();
+      for (int k = 0; k < parts; ++k) {
+        Part &p = part[k];
+        if (p.dead) continue;
+        const WaveBuffers &w = p.w;
+        const RenderCtx &R = p.R;
+        cudaStream_t st = p.st;
+        // Long walks (the reference accepts max_bounces up to 65535): once past 16 bounces, look at the path count every 8
+        // bounces and stop launching when the wave has died out (russian roulette empties it long before).
+        if (b >= 16 && (b & 7u) == 0) {
+          uint32_t alive = 0;
+          CUDA_TRY(cudaMemcpyAsync(&alive, w.counts + (size_t)b * Q_COUNT + N_PATHS, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+          CUDA_TRY(cudaStreamSynchronize(st));
+          if (alive == 0) {
+            p.dead = true;
+            continue;
           }
         }
-      }
-      if (P->light_samples > 0) {
-        T.begin(K_SHADOW);
-        launch_shadow(S, stats, cb);
+        p.bounces_run = b + 1;
+        uint32_t *cb = w.counts + (size_t)b * Q_COUNT, *cn = w.counts + (size_t)(b + 1) * Q_COUNT;
+        PathRec *in = w.paths[b & 1], *out = w.paths[(b + 1) & 1];
+        T.begin(K_TRACE);
+        if (tma)
+          launch_trace_tma(S, w, st, stats, in, cb);
+        else if (b == 0)
+          launch_trace<true>(S, w, st, stats, nullptr, cb, R, in);
+        else
+          launch_trace<false>(S, w, st, stats, in, cb, R, nullptr);
         T.end();
+        if (S->dev.env_kind != RPT_ENV_CONSTANT) {  // (a Constant environment's vertices are finished inside k_trace)
+          T.begin(K_SHADE_MISS);
+          k_shade_miss<<<S->grid[K_SHADE_MISS], 256, 0, st>>>(S->dev, in, w.q_miss, cb, w.acc);
+          T.end();
+        }
+        if (S->fused_shade) {
+          T.begin(K_SHADE_DIFFUSE);
+          k_shade_surface<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
+          T.end();
+          if (S->has_ggx) {  // (no GGX material in the scene: the class list stays empty, skip its 12 launches per wave)
+            T.begin(K_SHADE_GGX);
+            k_shade_surface<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.sh_a, w.sh_b, w.sh_c, w.acc);
+            T.end();
+          }
+        } else {
+          T.begin(K_SHADE_DIFFUSE);
+          k_shade_vertex<Q_DIFFUSE><<<S->grid[K_SHADE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, in, w.hits, w.q_diffuse, cb, cn, out, w.nee_d, w.acc);
+          T.end();
+          if (S->has_ggx) {
+            T.begin(K_SHADE_GGX);
+            k_shade_vertex<Q_GGX><<<S->grid[K_SHADE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, in, w.hits, w.q_ggx, cb, cn, out, w.nee_g, w.acc);
+            T.end();
+          }
+          if (P->light_samples > 0) {
+            T.begin(K_NEE_DIFFUSE);
+            k_nee<Q_DIFFUSE><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
+            T.end();
+            if (S->has_ggx) {
+              T.begin(K_NEE_GGX);
+              k_nee<Q_GGX><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
+              T.end();
+            }
+          }
+        }
+        if (P->light_samples > 0) {
+          T.begin(K_SHADOW);
+          launch_shadow(S, w, st, stats, cb);
+          T.end();
+        }
       }
     }
+    if (parts == 2) {  // join: the film pass of the wave reads both halves' energies
+      CUDA_TRY(cudaEventRecord(S->ev_join, S->stream2));
+      CUDA_TRY(cudaStreamWaitEvent(S->stream, S->ev_join, 0));
+    }
+    RenderCtx Rw = R0;  // the whole wave: the halves' energies are contiguous in acc
+    Rw.n_slots = (uint32_t)(wh * chunk);
+    Rw.sample_base = P->spp_offset + done;
     T.begin(K_FILM);
-    k_film<<<S->grid[K_FILM], 256, film_smem, S->stream>>>(S->dev, R, w.acc, S->film);
+    k_film<<<S->grid[K_FILM], 256, film_smem, S->stream>>>(S->dev, Rw, S->wave.acc, S->film);
     T.end();
-    CUDA_TRY(cudaMemcpyAsync(h_counts.data(), w.counts, n_counts * sizeof(uint32_t), cudaMemcpyDeviceToHost, S->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_counts.data(), S->wave.counts, h_counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, S->stream));
     CUDA_TRY(cudaStreamSynchronize(S->stream));
     CUDA_TRY(cudaGetLastError());
     // Profile counters (profile.rs:1-8) from the queue sizes
-    C.camera_rays += R.n_slots;
-    C.bounce_rays += R.n_slots;  // the camera vertex (pt.rs:465, integrator/utils.rs:375)
-    for (uint32_t b = 0; b < bounces_run; ++b) {
-      const uint32_t *c = &h_counts[(size_t)b * Q_COUNT];
-      C.segments += c[N_PATHS];
-      C.true_rays += c[N_PATHS] + c[N_SHADOW];
-      C.env_hits += c[N_MISS];
-      C.bounce_rays += c[N_MISS] + c[N_DIFFUSE] + c[N_GGX] - c[Q_NAN];
-      C.shadow_rays += c[Q_SHADOW_REF];
-      C.shadow_rays_traced += c[N_SHADOW];
-      C.nee_vertices += c[N_NEE];
-    }
+    C.camera_rays += Rw.n_slots;
+    C.bounce_rays += Rw.n_slots;  // the camera vertex (pt.rs:465, integrator/utils.rs:375)
+    for (int k = 0; k < parts; ++k)
+      for (uint32_t b = 0; b < part[k].bounces_run; ++b) {
+        const uint32_t *c = &h_counts[((size_t)k * rows + b) * Q_COUNT];
+        C.segments += c[N_PATHS];
+        C.true_rays += c[N_PATHS] + c[N_SHADOW];
+        C.env_hits += c[N_MISS];
+        C.bounce_rays += c[N_MISS] + c[N_DIFFUSE] + c[N_GGX] - c[Q_NAN];
+        C.shadow_rays += c[Q_SHADOW_REF];
+        C.shadow_rays_traced += c[N_SHADOW];
+        C.nee_vertices += c[N_NEE];
+      }
   }
   size_t ev_last = S->ev_used;
   cudaEventRecord(T.next_event(), S->stream);
-  unsigned long long h_work[6] = {0, 0, 0, 0, 0, 0};
-  if (stats) CUDA_TRY(cudaMemcpyAsync(h_work, w.work, sizeof(h_work), cudaMemcpyDeviceToHost, S->stream));
+  unsigned long long h_work[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (stats) CUDA_TRY(cudaMemcpyAsync(h_work, S->wave.work, sizeof(h_work), cudaMemcpyDeviceToHost, S->stream));
   CUDA_TRY(cudaStreamSynchronize(S->stream));
-  C.walk_nodes = h_work[0];
-  C.walk_tris = h_work[1];
-  C.walk_insts = h_work[2];
-  C.shadow_nodes = h_work[3];
-  C.shadow_tris = h_work[4];
-  C.shadow_insts = h_work[5];
+  C.walk_nodes = h_work[0] + h_work[6];
+  C.walk_tris = h_work[1] + h_work[7];
+  C.walk_insts = h_work[2] + h_work[8];
+  C.shadow_nodes = h_work[3] + h_work[9];
+  C.shadow_tris = h_work[4] + h_work[10];
+  C.shadow_insts = h_work[5] + h_work[11];
   {
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, S->ev_pool[ev_first], S->ev_pool[ev_last]);
@@ -2429,7 +2509,15 @@ int rpt_scene_destroy(RptScene *S) {
       sc.events.swap(S->ev_pool);
       S->stream = nullptr;
     }
+    if (S->stream2 && !sc.stream2) {
+      sc.stream2 = S->stream2;
+      sc.ev_join = S->ev_join;
+      S->stream2 = nullptr;
+      S->ev_join = nullptr;
+    }
   }
+  if (S->stream2) cudaStreamDestroy(S->stream2);
+  if (S->ev_join) cudaEventDestroy(S->ev_join);
   for (cudaEvent_t e : S->ev_pool) cudaEventDestroy(e);
   if (S->stream) cudaStreamDestroy(S->stream);
   delete S;
@@ -2930,9 +3018,9 @@ int rpt_trace_primary(RptScene *S, const RptRenderParams *P, uint32_t *inst, uin
   CUDA_TRY(cudaMemsetAsync(w.counts, 0, 2 * Q_COUNT * sizeof(uint32_t), S->stream));
   if (S->trav_mode == TRAV_BVH_TMA) {
     k_raygen<<<S->grid[K_RAYGEN], 256, 0, S->stream>>>(S->dev, R, w.paths[0], w.counts);
-    launch_trace_tma(S, false, w.paths[0], w.counts);
+    launch_trace_tma(S, w, S->stream, false, w.paths[0], w.counts);
   } else {
-    launch_trace<true>(S, false, nullptr, w.counts, R, w.paths[0]);
+    launch_trace<true>(S, w, S->stream, false, nullptr, w.counts, R, w.paths[0]);
   }
   std::vector<HitRec> h(wh);
   CUDA_TRY(cudaMemcpyAsync(h.data(), w.hits, wh * sizeof(HitRec), cudaMemcpyDeviceToHost, S->stream));
