@@ -156,26 +156,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // The tail a warp abandons (at most 31 entries when a chunk overflows, the rest of the chunk at kernel end) is
 // filled with invalid markers (RPT_NONE in the entry's first id word); consumers skip them. Chunk tails are
 // contiguous, so whole warps of the consumer skip together.
+// Chunk size follows the size of the kernel's INPUT queue: 256 entries for big launches, 32 for launches of fewer than
+// SMALL_QUEUE entries. With 256-entry chunks every one of the ~4 700 resident warps abandons on average half a chunk per
+// queue per launch; for the late bounces (0.5-3 M live paths) that padding was as large as the payload and the consumer of
+// the queue spent its time skipping it (a Cornell frame cost 1.9 ms + 1.17 ms per spp: most of the 1.9 was this).
 #define QCHUNK 256u
+#define QCHUNK_SMALL 32u
+#define SMALL_QUEUE (4u << 20)
 struct WarpChunk {
   uint32_t base, used;
 };
-__device__ __forceinline__ WarpChunk chunk_init() { return WarpChunk{0u, QCHUNK}; }
+__device__ __forceinline__ uint32_t chunk_size_for(uint32_t n_in) { return n_in >= SMALL_QUEUE ? QCHUNK : QCHUNK_SMALL; }
+__device__ __forceinline__ WarpChunk chunk_init(uint32_t cap = QCHUNK) { return WarpChunk{0u, cap}; }
 template <class Mark>
-__device__ __forceinline__ void chunk_pad(const WarpChunk &wc, Mark mark) {
-  for (uint32_t e = wc.used + (threadIdx.x & 31u); e < QCHUNK; e += 32u) mark(wc.base + e);
+__device__ __forceinline__ void chunk_pad(const WarpChunk &wc, Mark mark, uint32_t cap = QCHUNK) {
+  for (uint32_t e = wc.used + (threadIdx.x & 31u); e < cap; e += 32u) mark(wc.base + e);
 }
 // All 32 lanes must call. Returns this lane's entry index, or RPT_NONE if !pred.
 template <class Mark>
-__device__ __forceinline__ uint32_t chunk_append(uint32_t *counter, WarpChunk &wc, bool pred, Mark mark) {
+__device__ __forceinline__ uint32_t chunk_append(uint32_t *counter, WarpChunk &wc, bool pred, Mark mark, uint32_t cap = QCHUNK) {
   uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
   if (mask == 0) return RPT_NONE;
   uint32_t lane = threadIdx.x & 31u;
   uint32_t cnt = __popc(mask);
-  if (wc.used + cnt > QCHUNK) {  // warp-uniform
-    chunk_pad(wc, mark);
+  if (wc.used + cnt > cap) {  // warp-uniform
+    chunk_pad(wc, mark, cap);
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(counter, QCHUNK);
+    if (lane == 0) base = atomicAdd(counter, cap);
     wc.base = __shfl_sync(0xFFFFFFFFu, base, 0);
     wc.used = 0;
   }
@@ -189,8 +196,8 @@ __device__ __forceinline__ uint32_t chunk_append(uint32_t *counter, WarpChunk &w
 // kernels run 30 of 32 lanes on the coherent first bounce but 11-13 on unsorted later bounces.
 #define NBINS 8u
 #define QCHUNK_BINNED 128u
-template <uint32_t CH = QCHUNK_BINNED, class Mark>
-__device__ __forceinline__ uint32_t chunk_append_binned(uint32_t *counter, WarpChunk *st, bool pred, uint32_t bin, Mark mark) {
+template <class Mark>
+__device__ __forceinline__ uint32_t chunk_append_binned(uint32_t *counter, WarpChunk *st, bool pred, uint32_t bin, Mark mark, uint32_t CH = QCHUNK_BINNED) {
   uint32_t active = __ballot_sync(0xFFFFFFFFu, pred);
   uint32_t idx = RPT_NONE;
   if (pred) {
@@ -214,8 +221,8 @@ __device__ __forceinline__ uint32_t chunk_append_binned(uint32_t *counter, WarpC
   __syncwarp();
   return idx;
 }
-template <uint32_t CH = QCHUNK_BINNED, class Mark>
-__device__ __forceinline__ void chunk_pad_binned(const WarpChunk *st, uint32_t nbins, Mark mark) {
+template <class Mark>
+__device__ __forceinline__ void chunk_pad_binned(const WarpChunk *st, uint32_t nbins, Mark mark, uint32_t CH = QCHUNK_BINNED) {
   uint32_t lane = threadIdx.x & 31u;
   for (uint32_t b = 0; b < nbins; ++b) {
     WarpChunk wc = st[b];
@@ -392,9 +399,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
     __syncthreads();
   }
   TraceWork tw{0, 0, 0};
-  WarpChunk wc_miss = chunk_init(), wc_diffuse = chunk_init(), wc_ggx = chunk_init();
-  uint32_t n_miss = 0, n_diffuse = 0, n_ggx = 0;
   const uint32_t n = RAYGEN ? R.n_slots : counts[Q_PATHS];
+  const uint32_t qc = chunk_size_for(n);
+  WarpChunk wc_miss = chunk_init(qc), wc_diffuse = chunk_init(qc), wc_ggx = chunk_init(qc);
+  uint32_t n_miss = 0, n_diffuse = 0, n_ggx = 0;
   if (RAYGEN && blockIdx.x == 0 && threadIdx.x == 0) {
     counts[Q_PATHS] = n;
     counts[N_PATHS] = n;
@@ -491,11 +499,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
       hits[i] = h;
     }
     uint32_t k;
-    k = chunk_append(counts + Q_MISS, wc_miss, cls == Q_MISS, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
+    k = chunk_append(counts + Q_MISS, wc_miss, cls == Q_MISS, [&](uint32_t e) { q_miss[e] = RPT_NONE; }, qc);
     if (cls == Q_MISS) q_miss[k] = i;
-    k = chunk_append(counts + Q_DIFFUSE, wc_diffuse, cls == Q_DIFFUSE, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; });
+    k = chunk_append(counts + Q_DIFFUSE, wc_diffuse, cls == Q_DIFFUSE, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; }, qc);
     if (cls == Q_DIFFUSE) q_diffuse[k] = i;
-    k = chunk_append(counts + Q_GGX, wc_ggx, cls == Q_GGX, [&](uint32_t e) { q_ggx[e] = RPT_NONE; });
+    k = chunk_append(counts + Q_GGX, wc_ggx, cls == Q_GGX, [&](uint32_t e) { q_ggx[e] = RPT_NONE; }, qc);
     if (cls == Q_GGX) q_ggx[k] = i;
     n_miss += cls == Q_MISS;
     n_diffuse += cls == Q_DIFFUSE;
@@ -590,11 +598,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
           hits[my_i] = h;
         }
         uint32_t k;
-        k = chunk_append(counts + Q_MISS, wc_miss, cls == Q_MISS, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
+        k = chunk_append(counts + Q_MISS, wc_miss, cls == Q_MISS, [&](uint32_t e) { q_miss[e] = RPT_NONE; }, qc);
         if (cls == Q_MISS) q_miss[k] = my_i;
-        k = chunk_append(counts + Q_DIFFUSE, wc_diffuse, cls == Q_DIFFUSE, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; });
+        k = chunk_append(counts + Q_DIFFUSE, wc_diffuse, cls == Q_DIFFUSE, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; }, qc);
         if (cls == Q_DIFFUSE) q_diffuse[k] = my_i;
-        k = chunk_append(counts + Q_GGX, wc_ggx, cls == Q_GGX, [&](uint32_t e) { q_ggx[e] = RPT_NONE; });
+        k = chunk_append(counts + Q_GGX, wc_ggx, cls == Q_GGX, [&](uint32_t e) { q_ggx[e] = RPT_NONE; }, qc);
         if (cls == Q_GGX) q_ggx[k] = my_i;
         n_miss += cls == Q_MISS;
         n_diffuse += cls == Q_DIFFUSE;
@@ -608,9 +616,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
     ts.init(counts + F_TRACE, n_tiles, total_warps, S.min_grab);
     for (uint32_t tile = ts.next(); tile != RPT_NONE; tile = ts.next()) body(tile);
   }
-  if (wc_miss.used < QCHUNK) chunk_pad(wc_miss, [&](uint32_t e) { q_miss[e] = RPT_NONE; });
-  if (wc_diffuse.used < QCHUNK) chunk_pad(wc_diffuse, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; });
-  if (wc_ggx.used < QCHUNK) chunk_pad(wc_ggx, [&](uint32_t e) { q_ggx[e] = RPT_NONE; });
+  if (wc_miss.used < qc) chunk_pad(wc_miss, [&](uint32_t e) { q_miss[e] = RPT_NONE; }, qc);
+  if (wc_diffuse.used < qc) chunk_pad(wc_diffuse, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; }, qc);
+  if (wc_ggx.used < qc) chunk_pad(wc_ggx, [&](uint32_t e) { q_ggx[e] = RPT_NONE; }, qc);
   flush_count(n_miss, counts + N_MISS);
   flush_count(n_diffuse, counts + N_DIFFUSE);
   flush_count(n_ggx, counts + N_GGX);
@@ -682,9 +690,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
   // keeps a single register-resident chunk (binning walk rays by direction octant was measured: no gain)
   __shared__ WarpChunk s_chunks[SHADE_THREADS / 32][NBINS];
   WarpChunk *st_shadow = s_chunks[threadIdx.x >> 5];
-  if ((threadIdx.x & 31u) < NBINS) st_shadow[threadIdx.x & 31u] = WarpChunk{0u, QCHUNK_BINNED};
+  const uint32_t qc = chunk_size_for(n), bc = n >= BIN_MIN_ITEMS ? QCHUNK_BINNED : QCHUNK_SMALL;
+  WarpChunk wc_next = chunk_init(qc);
+  if ((threadIdx.x & 31u) < NBINS) st_shadow[threadIdx.x & 31u] = WarpChunk{0u, bc};
   __syncwarp();
-  WarpChunk wc_next = chunk_init();
   const uint32_t nbins = n >= BIN_MIN_ITEMS ? NBINS : 1u;  // small queues: binning would only scatter a few rays over many chunks
   uint32_t n_next = 0, n_shadow = 0, n_sh_ref = 0, n_nan = 0;
   auto mark_next = [&](uint32_t e) { out[e].r3 = make_float4(__uint_as_float(RPT_NONE), 0.0f, 0.0f, 0.0f); };
@@ -819,7 +828,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
       }
     }
     // ---- next path queue: one atomic per warp
-    uint32_t k = chunk_append(next_counts + Q_PATHS, wc_next, continues, mark_next);
+    uint32_t k = chunk_append(next_counts + Q_PATHS, wc_next, continues, mark_next, qc);
     if (continues) out[k] = nr;
     n_next += continues;
 
@@ -889,7 +898,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
           }
         }
         uint32_t bin_sh = nbins > 1 ? ((a.x < S.world_center.x) | ((a.y < S.world_center.y) << 1) | ((a.z < S.world_center.z) << 2)) : 0u;  // origin cell
-        uint32_t q = chunk_append_binned(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow);
+        uint32_t q = chunk_append_binned(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow, bc);
         if (has) {
           sh_a[q] = a;
           sh_b[q] = b4;
@@ -905,8 +914,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
     t_next = t_nn;
   }
   cp_async_wait<0>();
-  if (wc_next.used < QCHUNK) chunk_pad(wc_next, mark_next);
-  chunk_pad_binned(st_shadow, NBINS, mark_shadow);
+  if (wc_next.used < qc) chunk_pad(wc_next, mark_next, qc);
+  chunk_pad_binned(st_shadow, NBINS, mark_shadow, bc);
   flush_count(n_next, next_counts + N_PATHS);
   flush_count(n_shadow, counts + N_SHADOW);
   flush_count(n_sh_ref, counts + Q_SHADOW_REF);  // reference-definition shadow-ray counter (pt.rs:176,252)
@@ -953,7 +962,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, VERTEX_MIN_BLOCKS) k_shade_vert
     }
     cp_async_commit();
   };
-  WarpChunk wc_next = chunk_init(), wc_nee = chunk_init();
+  const uint32_t qc = chunk_size_for(n);
+  WarpChunk wc_next = chunk_init(qc), wc_nee = chunk_init(qc);
   uint32_t n_next = 0, n_nee = 0, n_nan = 0;
   auto mark_next = [&](uint32_t e) { out[e].r3 = make_float4(__uint_as_float(RPT_NONE), 0.0f, 0.0f, 0.0f); };
   auto mark_nee = [&](uint32_t e) { nee[e].r2 = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RPT_NONE)); };
@@ -1062,8 +1072,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, VERTEX_MIN_BLOCKS) k_shade_vert
         continues = nbeta != 0.0f && !(s.z > rr) && bounce + 1 < max_bounces;
       }
     }
-    const uint32_t k_next = chunk_append(next_counts + Q_PATHS, wc_next, continues, mark_next);
-    const uint32_t k_nee = chunk_append(nee_counter, wc_nee, do_nee, mark_nee);
+    const uint32_t k_next = chunk_append(next_counts + Q_PATHS, wc_next, continues, mark_next, qc);
+    const uint32_t k_nee = chunk_append(nee_counter, wc_nee, do_nee, mark_nee, qc);
     n_next += continues;
     n_nee += do_nee;
     if (continues || do_nee) {
@@ -1092,8 +1102,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, VERTEX_MIN_BLOCKS) k_shade_vert
     t_next = t_nn;
   }
   cp_async_wait<0>();
-  if (wc_next.used < QCHUNK) chunk_pad(wc_next, mark_next);
-  if (wc_nee.used < QCHUNK) chunk_pad(wc_nee, mark_nee);
+  if (wc_next.used < qc) chunk_pad(wc_next, mark_next, qc);
+  if (wc_nee.used < qc) chunk_pad(wc_nee, mark_nee, qc);
   flush_count(n_next, next_counts + N_PATHS);
   flush_count(n_nee, counts + N_NEE);
   flush_count(n_nan, counts + Q_NAN);
@@ -1118,9 +1128,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
                                                          uint32_t *__restrict__ sh_c) {
   __shared__ WarpChunk s_chunks[SHADE_THREADS / 32][NEE_BINS];
   WarpChunk *st_shadow = s_chunks[threadIdx.x >> 5];
-  for (uint32_t b = threadIdx.x & 31u; b < NEE_BINS; b += 32u) st_shadow[b] = WarpChunk{0u, NEE_CHUNK};
-  __syncwarp();
   const uint32_t n = counts[CLASS == Q_DIFFUSE ? Q_NEE_DIFFUSE : Q_NEE_GGX];
+  const uint32_t bc = n >= BIN_MIN_ITEMS ? NEE_CHUNK : QCHUNK_SMALL;
+  for (uint32_t b = threadIdx.x & 31u; b < NEE_BINS; b += 32u) st_shadow[b] = WarpChunk{0u, bc};
+  __syncwarp();
   const uint32_t L = R.light_samples;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_tiles = (n + 31u) >> 5;
@@ -1225,7 +1236,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
         uint32_t cz = (uint32_t)fminf(fmaxf((a.z - S.world_min.z) * S.world_inv_extent.z * g, 0.0f), g - 1.0f);
         bin_sh = (cz * NEE_GRID + cy) * NEE_GRID + cx;
       }
-      uint32_t q = chunk_append_binned<NEE_CHUNK>(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow);
+      uint32_t q = chunk_append_binned(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow, bc);
       if (has) {
         sh_a[q] = a;
         sh_b[q] = b4;
@@ -1234,7 +1245,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
       n_shadow += has;
     }
   }
-  chunk_pad_binned<NEE_CHUNK>(st_shadow, NEE_BINS, mark_shadow);
+  chunk_pad_binned(st_shadow, NEE_BINS, mark_shadow, bc);
   flush_count(n_shadow, counts + N_SHADOW);
   flush_count(n_sh_ref, counts + Q_SHADOW_REF);  // reference-definition shadow-ray counter (pt.rs:176,252)
 }
@@ -2022,14 +2033,15 @@ size_t path_queue_cap(const RptScene *S, size_t valid) {  // next-path queue, cl
   size_t shade_warps = ((size_t)S->grid[K_SHADE_DIFFUSE] + (size_t)S->grid[K_SHADE_GGX]) * (SHADE_THREADS / 32);
   size_t trace_warps = (size_t)S->grid[K_TRACE] * (TRACE_THREADS / 32);
   size_t tail = std::max(shade_warps, trace_warps) * QCHUNK;
-  return valid + (valid * 31 + (QCHUNK - 31) - 1) / (QCHUNK - 31) + tail + QCHUNK;
+  // (+ min(valid, SMALL_QUEUE): launches below SMALL_QUEUE entries use 32-entry chunks, whose worst case doubles the queue)
+  return valid + (valid * 31 + (QCHUNK - 31) - 1) / (QCHUNK - 31) + std::min<size_t>(valid, SMALL_QUEUE) + tail + QCHUNK;
 }
 size_t shadow_queue_cap(const RptScene *S, size_t valid) {
   size_t shade_warps = ((size_t)std::max(S->grid[K_SHADE_DIFFUSE], S->grid[K_NEE_DIFFUSE]) + (size_t)std::max(S->grid[K_SHADE_GGX], S->grid[K_NEE_GGX])) * (SHADE_THREADS / 32);
   const size_t bins = std::max<size_t>(NBINS, NEE_BINS), chunk = std::min<size_t>(QCHUNK_BINNED, NEE_CHUNK);
   size_t tail = shade_warps * std::max<size_t>((size_t)NBINS * QCHUNK_BINNED, (size_t)NEE_BINS * NEE_CHUNK);
   (void)bins;
-  return valid + (valid * 31 + (chunk - 31) - 1) / (chunk - 31) + tail + QCHUNK_BINNED;
+  return valid + (valid * 31 + (chunk - 31) - 1) / (chunk - 31) + std::min<size_t>(valid, BIN_MIN_ITEMS) + tail + QCHUNK_BINNED;
 }
 // The wave buffers are provisioned for TWO half-waves (render_waves runs the two halves of a wave on two streams so that the
 // ragged tail of one half's launches overlaps the other half's work): each queue holds twice the capacity of half the slots.
@@ -2266,14 +2278,14 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   std::vector<uint32_t> h_counts(2 * rows * Q_COUNT);
   RptCounters C{};
   size_t film_smem = 3 * (size_t)S->dev.num_lambda * sizeof(float);
-  // Two half-waves on two streams: every kernel of the pipeline is a persistent grid that fills the machine, and every
-  // launch ends in a ragged tail where SMs run dry one by one while the last tiles finish (a 16 spp Cornell frame costs
-  // 20.7 ms, one eighth of a 128 spp frame 18.8 ms: ~2 ms of tails and fixed costs per 49 launches). With the wave cut in
-  // two independent halves (disjoint sample ranges, disjoint halves of every queue) on two streams, the CTAs of the other
-  // half's pending launch move in as soon as a tail frees SMs. Off when per-kernel timing is on (the spans would overlap),
-  // for 1-spp waves, and with RPT_NO_OVERLAP=1.
-  const char *no_ov = std::getenv("RPT_NO_OVERLAP");
-  const bool overlap_ok = !T.timed && !(no_ov && no_ov[0] == '1');
+  // Opt-in (RPT_OVERLAP=1): two half-waves on two streams. The idea: every launch of a persistent grid ends in a ragged tail
+  // where SMs run dry while the last tiles finish; with the wave cut in two independent halves (disjoint sample ranges,
+  // disjoint halves of every queue) on two streams, the CTAs of the other half's pending launch could move in as soon as a
+  // tail frees SMs. Measured (profiles/r02_overlap.md): slower everywhere - Cornell 21.5 vs 20.6 ms, kitchen_sink 8.1 vs
+  // 6.8 ms: twice the launches, and two grids that each fill the machine only take turns. The fixed cost it was after turned
+  // out to be chunk padding (see QCHUNK_SMALL). Never on when per-kernel timing is on (the spans would overlap).
+  const char *ov = std::getenv("RPT_OVERLAP");
+  const bool overlap_ok = !T.timed && ov && ov[0] == '1';
   if (overlap_ok && !S->stream2) {
     {
       std::lock_guard<std::mutex> lk(g_cache_mu);
