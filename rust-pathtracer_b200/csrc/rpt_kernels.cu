@@ -161,8 +161,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // queue per launch; for the late bounces (0.5-3 M live paths) that padding was as large as the payload and the consumer of
 // the queue spent its time skipping it (a Cornell frame cost 1.9 ms + 1.17 ms per spp: most of the 1.9 was this).
 #define QCHUNK 256u
+#ifndef QCHUNK_SMALL
 #define QCHUNK_SMALL 32u
+#endif
+#ifndef QCHUNK_BINNED_SMALL
+#define QCHUNK_BINNED_SMALL 32u
+#endif
+#ifndef SMALL_QUEUE
 #define SMALL_QUEUE (4u << 20)
+#endif
 struct WarpChunk {
   uint32_t base, used;
 };
@@ -690,7 +697,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
   // keeps a single register-resident chunk (binning walk rays by direction octant was measured: no gain)
   __shared__ WarpChunk s_chunks[SHADE_THREADS / 32][NBINS];
   WarpChunk *st_shadow = s_chunks[threadIdx.x >> 5];
-  const uint32_t qc = chunk_size_for(n), bc = n >= BIN_MIN_ITEMS ? QCHUNK_BINNED : QCHUNK_SMALL;
+  const uint32_t qc = chunk_size_for(n), bc = n >= BIN_MIN_ITEMS ? QCHUNK_BINNED : QCHUNK_BINNED_SMALL;
   WarpChunk wc_next = chunk_init(qc);
   if ((threadIdx.x & 31u) < NBINS) st_shadow[threadIdx.x & 31u] = WarpChunk{0u, bc};
   __syncwarp();
@@ -1129,7 +1136,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
   __shared__ WarpChunk s_chunks[SHADE_THREADS / 32][NEE_BINS];
   WarpChunk *st_shadow = s_chunks[threadIdx.x >> 5];
   const uint32_t n = counts[CLASS == Q_DIFFUSE ? Q_NEE_DIFFUSE : Q_NEE_GGX];
-  const uint32_t bc = n >= BIN_MIN_ITEMS ? NEE_CHUNK : QCHUNK_SMALL;
+  const uint32_t bc = n >= BIN_MIN_ITEMS ? NEE_CHUNK : QCHUNK_BINNED_SMALL;
   for (uint32_t b = threadIdx.x & 31u; b < NEE_BINS; b += 32u) st_shadow[b] = WarpChunk{0u, bc};
   __syncwarp();
   const uint32_t L = R.light_samples;
