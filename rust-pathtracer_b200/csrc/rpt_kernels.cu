@@ -156,16 +156,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // The tail a warp abandons (at most 31 entries when a chunk overflows, the rest of the chunk at kernel end) is
 // filled with invalid markers (RPT_NONE in the entry's first id word); consumers skip them. Chunk tails are
 // contiguous, so whole warps of the consumer skip together.
-// Chunk size follows the size of the kernel's INPUT queue: 256 entries for big launches, 32 for launches of fewer than
-// SMALL_QUEUE entries. With 256-entry chunks every one of the ~4 700 resident warps abandons on average half a chunk per
-// queue per launch; for the late bounces (0.5-3 M live paths) that padding was as large as the payload and the consumer of
-// the queue spent its time skipping it (a Cornell frame cost 1.9 ms + 1.17 ms per spp: most of the 1.9 was this).
+// Chunk size may follow the size of the kernel's INPUT queue (QCHUNK_SMALL / QCHUNK_BINNED_SMALL for launches of fewer
+// than SMALL_QUEUE / BIN_MIN_ITEMS entries). With 256-entry chunks every one of the ~4 700 resident warps abandons on
+// average half a chunk per queue per launch, and for the late bounces (0.5-3 M live paths) that padding is as large as the
+// payload. Measured in one session (profiles/r02_chunk_policy.md): 32-entry chunks below 4 M entries help a 512x384 frame
+// (7.12 -> 6.55 ms) but cost the 1080p Cornell frame 7 % (20.99 -> 22.43 ms; the vertex kernel 3.97 -> 4.77 ms) and the gem
+// 3 %: four times the same-address atomicAdds on the queue counters outweigh the padding. The defaults therefore keep one
+// chunk size; the policy stays compiled in for the record (-DQCHUNK_SMALL=32u -DQCHUNK_BINNED_SMALL=32u).
 #define QCHUNK 256u
 #ifndef QCHUNK_SMALL
-#define QCHUNK_SMALL 32u
+#define QCHUNK_SMALL 256u
 #endif
 #ifndef QCHUNK_BINNED_SMALL
-#define QCHUNK_BINNED_SMALL 32u
+#define QCHUNK_BINNED_SMALL 128u
 #endif
 #ifndef SMALL_QUEUE
 #define SMALL_QUEUE (4u << 20)
