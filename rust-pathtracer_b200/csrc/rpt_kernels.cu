@@ -2053,10 +2053,16 @@ size_t shadow_queue_cap(const RptScene *S, size_t valid) {
   (void)bins;
   return valid + (valid * 31 + (chunk - 31) - 1) / (chunk - 31) + std::min<size_t>(valid, BIN_MIN_ITEMS) + tail + QCHUNK_BINNED;
 }
-// The wave buffers are provisioned for TWO half-waves (render_waves runs the two halves of a wave on two streams so that the
-// ragged tail of one half's launches overlaps the other half's work): each queue holds twice the capacity of half the slots.
-size_t wave_path_cap(const RptScene *S, size_t slots) { return 2 * path_queue_cap(S, (slots + 1) / 2); }
-size_t wave_shadow_cap(const RptScene *S, size_t shadow_valid) { return 2 * shadow_queue_cap(S, (shadow_valid + 1) / 2); }
+// With RPT_OVERLAP=1 the wave buffers are provisioned for TWO half-waves (render_waves then runs the two halves of a wave on
+// two streams): each queue holds twice the capacity of half the slots.
+bool overlap_enabled() {  // RPT_OVERLAP=1 (opt-in, see render_waves)
+  const char *ov = std::getenv("RPT_OVERLAP");
+  return ov && ov[0] == '1';
+}
+size_t wave_path_cap(const RptScene *S, size_t slots) { return overlap_enabled() ? 2 * path_queue_cap(S, (slots + 1) / 2) : path_queue_cap(S, slots); }
+size_t wave_shadow_cap(const RptScene *S, size_t shadow_valid) {
+  return overlap_enabled() ? 2 * shadow_queue_cap(S, (shadow_valid + 1) / 2) : shadow_queue_cap(S, shadow_valid);
+}
 constexpr size_t kPathSlotBytes = 2 * sizeof(PathRec) + sizeof(HitRec) + 3 * sizeof(uint32_t) + 2 * sizeof(NeeRec);
 constexpr size_t kShadowSlotBytes = 2 * sizeof(float4) + sizeof(uint32_t);
 size_t wave_bytes(const RptScene *S, size_t slots, uint32_t light_samples) {
@@ -2294,8 +2300,7 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   // tail frees SMs. Measured (profiles/r02_overlap.md): slower everywhere - Cornell 21.5 vs 20.6 ms, kitchen_sink 8.1 vs
   // 6.8 ms: twice the launches, and two grids that each fill the machine only take turns. The fixed cost it was after turned
   // out to be chunk padding (see QCHUNK_SMALL). Never on when per-kernel timing is on (the spans would overlap).
-  const char *ov = std::getenv("RPT_OVERLAP");
-  const bool overlap_ok = !T.timed && ov && ov[0] == '1';
+  const bool overlap_ok = !T.timed && overlap_enabled();
   if (overlap_ok && !S->stream2) {
     {
       std::lock_guard<std::mutex> lk(g_cache_mu);

@@ -526,6 +526,25 @@ def test_lane_refill_mode_equals_tile_mode(monkeypatch, name):
     refill.close()
 
 
+@pytest.mark.parametrize("name", ["cornell", "kitchen_sink", "hdri2"])
+def test_two_stream_half_waves_equal_single_stream(monkeypatch, name):
+    """RPT_OVERLAP=1 (a wave cut into two half-waves on two streams; opt-in after measurement, profiles/r02_overlap.md) renders
+    the same samples: identical counters, film equal up to the order of the f32 sums."""
+    world, st, flat = parity.load_scene(name, 160, 90, 5)
+    single = parity.cuda_scene(flat)
+    f0, c0 = single.render_pt(st.params(seed=23))
+    single.close()
+    monkeypatch.setenv("RPT_OVERLAP", "1")
+    two = parity.cuda_scene(flat)
+    f1, c1 = two.render_pt(st.params(seed=23))
+    two.close()
+    for k in ("camera_rays", "segments", "bounce_rays", "shadow_rays", "shadow_rays_traced", "env_hits", "nee_vertices"):
+        assert getattr(c0, k) == getattr(c1, k), (name, k)
+    assert c1.kernel_launches > c0.kernel_launches  # (two launches per kernel and bounce)
+    ok = np.isfinite(f0)
+    assert np.array_equal(ok, np.isfinite(f1)) and np.allclose(f0[ok], f1[ok], rtol=1e-5, atol=1e-9)
+
+
 def test_reference_parameter_ranges(scenes):
     """The reference takes any u16 for light_samples and max_bounces (parsing/config.rs:22-23); so does the library
     (round 1 rejected light_samples > 8 and max_bounces > 64)."""
