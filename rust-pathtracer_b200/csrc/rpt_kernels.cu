@@ -246,6 +246,33 @@ __device__ __forceinline__ void flush_count(uint32_t v, uint32_t *dst) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
   if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, v);
 }
+// The same for N counters at once, reduced over the whole CTA first: one atomic per CTA and counter instead of one per warp.
+// The counters of a bounce share a cache line, and ~4 700 warps x 3-4 counters of same-line atomics at the end of EVERY launch
+// (~1.4 ns each at the L2) were a measurable part of the 50-90 us floor of the small late-bounce launches.
+// Every thread of the CTA must call it (it synchronises).
+template <int N>
+__device__ __forceinline__ void flush_counts_cta(const uint32_t (&v)[N], uint32_t *const (&dst)[N]) {
+#ifdef RPT_PER_WARP_FLUSH  // A/B switch: the round-1 form, one atomic per warp and counter
+#pragma unroll
+  for (int k = 0; k < N; ++k) flush_count(v[k], dst[k]);
+  return;
+#endif
+  __shared__ uint32_t s_cnt[N][32];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, nwarps = (blockDim.x + 31u) >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    uint32_t x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+    if (lane == 0) s_cnt[k][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    uint32_t x = 0;
+    for (uint32_t w = 0; w < nwarps; ++w) x += s_cnt[threadIdx.x][w];
+    if (x) atomicAdd(dst[threadIdx.x], x);
+  }
+}
 
 // Dynamic hand-out of a queue's tiles (32 consecutive entries each) to warps. Rays cost 1..30 node visits and vertices
 // differ in their NEE work, so with a static split the warps of a launch finish far apart (ncu: achieved occupancy 41 of a
@@ -629,9 +656,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
   if (wc_miss.used < qc) chunk_pad(wc_miss, [&](uint32_t e) { q_miss[e] = RPT_NONE; }, qc);
   if (wc_diffuse.used < qc) chunk_pad(wc_diffuse, [&](uint32_t e) { q_diffuse[e] = RPT_NONE; }, qc);
   if (wc_ggx.used < qc) chunk_pad(wc_ggx, [&](uint32_t e) { q_ggx[e] = RPT_NONE; }, qc);
-  flush_count(n_miss, counts + N_MISS);
-  flush_count(n_diffuse, counts + N_DIFFUSE);
-  flush_count(n_ggx, counts + N_GGX);
+  {
+    const uint32_t v[3] = {n_miss, n_diffuse, n_ggx};
+    uint32_t *const d[3] = {counts + N_MISS, counts + N_DIFFUSE, counts + N_GGX};
+    flush_counts_cta<3>(v, d);
+  }
   if (STATS) flush_work(tw, work);
 }
 
@@ -926,10 +955,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
   cp_async_wait<0>();
   if (wc_next.used < qc) chunk_pad(wc_next, mark_next, qc);
   chunk_pad_binned(st_shadow, NBINS, mark_shadow, bc);
-  flush_count(n_next, next_counts + N_PATHS);
-  flush_count(n_shadow, counts + N_SHADOW);
-  flush_count(n_sh_ref, counts + Q_SHADOW_REF);  // reference-definition shadow-ray counter (pt.rs:176,252)
-  flush_count(n_nan, counts + Q_NAN);
+  {
+    const uint32_t v[4] = {n_next, n_shadow, n_sh_ref, n_nan};  // Q_SHADOW_REF: reference-definition shadow-ray counter (pt.rs:176,252)
+    uint32_t *const d[4] = {next_counts + N_PATHS, counts + N_SHADOW, counts + Q_SHADOW_REF, counts + Q_NAN};
+    flush_counts_cta<4>(v, d);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1114,9 +1144,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, VERTEX_MIN_BLOCKS) k_shade_vert
   cp_async_wait<0>();
   if (wc_next.used < qc) chunk_pad(wc_next, mark_next, qc);
   if (wc_nee.used < qc) chunk_pad(wc_nee, mark_nee, qc);
-  flush_count(n_next, next_counts + N_PATHS);
-  flush_count(n_nee, counts + N_NEE);
-  flush_count(n_nan, counts + Q_NAN);
+  {
+    const uint32_t v[3] = {n_next, n_nee, n_nan};
+    uint32_t *const d[3] = {next_counts + N_PATHS, counts + N_NEE, counts + Q_NAN};
+    flush_counts_cta<3>(v, d);
+  }
 }
 
 // NEE sample generation for the vertices k_shade_vertex handed over (estimate_direct_illumination_with_loop, pt.rs:333-393;
@@ -1256,8 +1288,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
     }
   }
   chunk_pad_binned(st_shadow, NEE_BINS, mark_shadow, bc);
-  flush_count(n_shadow, counts + N_SHADOW);
-  flush_count(n_sh_ref, counts + Q_SHADOW_REF);  // reference-definition shadow-ray counter (pt.rs:176,252)
+  {
+    const uint32_t v[2] = {n_shadow, n_sh_ref};  // Q_SHADOW_REF: reference-definition shadow-ray counter (pt.rs:176,252)
+    uint32_t *const d[2] = {counts + N_SHADOW, counts + Q_SHADOW_REF};
+    flush_counts_cta<2>(v, d);
+  }
 }
 
 // Phase A of the two-phase NEE visibility query: the closest hit among the scene's few analytic light-material shapes
@@ -2257,6 +2292,11 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   if (want_slots < ((size_t)1 << 30) && wave_path_cap(S, want_slots) <= S->wave_slots &&
       wave_shadow_cap(S, want_slots * P->light_samples) <= S->wave_shadow && want_slots <= S->wave_acc && max_bounces <= S->counts_cap) {
     spp_chunk = std::max<uint32_t>(P->spp, 1);
+  } else if (S->wave_acc >= wh && wave_path_cap(S, (S->wave_acc / wh) * wh) <= S->wave_slots &&
+             wave_shadow_cap(S, (S->wave_acc / wh) * wh * P->light_samples) <= S->wave_shadow && max_bounces <= S->counts_cap) {
+    // a job larger than one wave whose wave buffers already exist (the previous frame of a frame loop): keep their size; the
+    // memory query below costs tens of milliseconds in a process that holds ~100 GB (seen as 90 vs 60 ms per 128 spp furnace frame)
+    spp_chunk = (uint32_t)std::min<size_t>(std::max<uint32_t>(P->spp, 1), S->wave_acc / wh);
   } else {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
