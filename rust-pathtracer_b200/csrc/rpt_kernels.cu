@@ -246,17 +246,16 @@ __device__ __forceinline__ void flush_count(uint32_t v, uint32_t *dst) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
   if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, v);
 }
-// The same for N counters at once, reduced over the whole CTA first: one atomic per CTA and counter instead of one per warp.
-// The counters of a bounce share a cache line, and ~4 700 warps x 3-4 counters of same-line atomics at the end of EVERY launch
-// (~1.4 ns each at the L2) were a measurable part of the 50-90 us floor of the small late-bounce launches.
-// Every thread of the CTA must call it (it synchronises).
+// The same for N counters at once. -DRPT_CTA_FLUSH reduces over the whole CTA first (one atomic per CTA and counter instead
+// of one per warp): tried because ~4 700 warps x 3-4 same-line atomics end every launch; measured in one session
+// (profiles/r02_flush_variants.txt) it changes nothing on Cornell (20.69 vs 20.67 ms) and costs the all-GGX furnace 4 %
+// (the extra __syncthreads at the end of k_nee), so the per-warp form stays the default.
 template <int N>
 __device__ __forceinline__ void flush_counts_cta(const uint32_t (&v)[N], uint32_t *const (&dst)[N]) {
-#ifdef RPT_PER_WARP_FLUSH  // A/B switch: the round-1 form, one atomic per warp and counter
+#ifndef RPT_CTA_FLUSH
 #pragma unroll
   for (int k = 0; k < N; ++k) flush_count(v[k], dst[k]);
-  return;
-#endif
+#else
   __shared__ uint32_t s_cnt[N][32];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, nwarps = (blockDim.x + 31u) >> 5;
 #pragma unroll
@@ -272,6 +271,7 @@ __device__ __forceinline__ void flush_counts_cta(const uint32_t (&v)[N], uint32_
     for (uint32_t w = 0; w < nwarps; ++w) x += s_cnt[threadIdx.x][w];
     if (x) atomicAdd(dst[threadIdx.x], x);
   }
+#endif
 }
 
 // Dynamic hand-out of a queue's tiles (32 consecutive entries each) to warps. Rays cost 1..30 node visits and vertices
