@@ -1968,6 +1968,8 @@ struct RptScene {
   int trav_mode = TRAV_BVH;  // TRAV_SMALL (RPT_SMALL=1) for scenes of <= RPT_SMALL_MAX leaves without a BLAS;
                              // TRAV_BVH_TMA: k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
   size_t counts_cap = 0;     // bounces the per-bounce counter block has room for
+  size_t budget_slots = 0;   // camera samples one wave may hold (from the last memory query), for budget_light_samples
+  uint32_t budget_light_samples = 0;
   // timing of the last render
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -2292,11 +2294,10 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   if (want_slots < ((size_t)1 << 30) && wave_path_cap(S, want_slots) <= S->wave_slots &&
       wave_shadow_cap(S, want_slots * P->light_samples) <= S->wave_shadow && want_slots <= S->wave_acc && max_bounces <= S->counts_cap) {
     spp_chunk = std::max<uint32_t>(P->spp, 1);
-  } else if (S->wave_acc >= wh && wave_path_cap(S, (S->wave_acc / wh) * wh) <= S->wave_slots &&
-             wave_shadow_cap(S, (S->wave_acc / wh) * wh * P->light_samples) <= S->wave_shadow && max_bounces <= S->counts_cap) {
-    // a job larger than one wave whose wave buffers already exist (the previous frame of a frame loop): keep their size; the
-    // memory query below costs tens of milliseconds in a process that holds ~100 GB (seen as 90 vs 60 ms per 128 spp furnace frame)
-    spp_chunk = (uint32_t)std::min<size_t>(std::max<uint32_t>(P->spp, 1), S->wave_acc / wh);
+  } else if (S->budget_slots && S->budget_light_samples == P->light_samples && wh <= S->budget_slots) {
+    // the wave budget of this scene is known from an earlier call with the same light_samples: the memory query below costs
+    // tens of milliseconds in a process that holds ~100 GB (seen as 90 vs 60 ms per 128 spp furnace frame in a frame loop)
+    spp_chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(P->spp ? P->spp : 1, S->budget_slots / wh));
   } else {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -2314,6 +2315,8 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
     if (budget <= fixed) return fail("not enough device memory for the wave queues");
     size_t max_slots = std::min<size_t>((budget - fixed) / per_1k * 1024, (size_t)1 << 30);
     if (wh > max_slots) return fail("film does not fit one wave");
+    S->budget_slots = max_slots;
+    S->budget_light_samples = P->light_samples;
     spp_chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(P->spp ? P->spp : 1, max_slots / wh));
   }
   if (const char *e = std::getenv("RPT_WAVE_SLOTS_MAX")) {  // test hook: force several waves on a job that would fit one
@@ -2321,7 +2324,10 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
     if (cap >= wh) spp_chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(spp_chunk, cap / wh));
   }
   size_t slots = wh * spp_chunk;
-  if (int rc = ensure_wave(S, slots, slots * P->light_samples, max_bounces)) return rc;
+  if (int rc = ensure_wave(S, slots, slots * P->light_samples, max_bounces)) {
+    S->budget_slots = 0;  // (the cached budget may be stale: the next call queries the memory again)
+    return rc;
+  }
 
   S->ev_used = 0;
   S->spans.clear();

@@ -1,22 +1,22 @@
 #!/bin/bash
-# Round 2, GPU call O (8 GPUs): final scaling table, all N on one box, shipped build.
+# Round 2, GPU call P (8 GPUs): final scaling table, all N on one box, shipped build.
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/r02o_gpu.txt
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k "multi_device" > gpurun_out/r02o_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02o_pytest.log
-port=29530
+nvidia-smi -L > gpurun_out/r02p_gpu.txt
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k "multi_device" > gpurun_out/r02p_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02p_pytest.log
+port=29540
 for n in 8 4 2; do
   port=$((port+1))
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/r02o_bench_n$n.json 2> gpurun_out/r02o_bench_n$n.err
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/r02p_bench_n$n.json 2> gpurun_out/r02p_bench_n$n.err
 done
-timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/r02o_bench_n1.json 2> gpurun_out/r02o_bench_n1.err
+timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/r02p_bench_n1.json 2> gpurun_out/r02p_bench_n1.err
 set +x
-tail -3 gpurun_out/r02o_pytest.log
+tail -3 gpurun_out/r02p_pytest.log
 python - <<'PY'
 import json
 for n in (1, 2, 4, 8):
-    f = f"gpurun_out/r02o_bench_n{n}.json"
+    f = f"gpurun_out/r02p_bench_n{n}.json"
     try:
         j = json.loads(open(f).read().strip().splitlines()[-1])
     except Exception as e:
