@@ -246,4 +246,84 @@ BuiltBvh build_bvh(const std::vector<Box> &shapes) {
   return std::move(b.out);
 }
 
+namespace {
+
+struct Collapser {
+  const BuiltBvh &in;
+  WideBvh out;
+  struct Slot {
+    Box box;
+    int32_t ref;
+  };
+  static float half_area(const Box &b) {
+    float sx = b.mx[0] - b.mn[0], sy = b.mx[1] - b.mn[1], sz = b.mx[2] - b.mn[2];
+    return sx * sy + sx * sz + sy * sz;
+  }
+  static void children_of(const HostNode &n, Slot &l, Slot &r) {
+    for (int k = 0; k < 3; ++k) {
+      l.box.mn[k] = n.lmin[k];
+      l.box.mx[k] = n.lmax[k];
+      r.box.mn[k] = n.rmin[k];
+      r.box.mx[k] = n.rmax[k];
+    }
+    l.ref = n.left;
+    r.ref = n.right;
+  }
+  // returns the wide child-ref of two-wide ref `ref`; *need = stack entries the walk below it can hold
+  int32_t convert(int32_t ref, uint32_t *need) {
+    if (ref < 0) {
+      *need = 0;
+      return ref;
+    }
+    Slot s[4];
+    int n = 2;
+    children_of(in.nodes[ref], s[0], s[1]);
+    while (n < 4) {
+      int pick = -1;
+      float best = -1.0f;
+      for (int i = 0; i < n; ++i) {
+        if (s[i].ref < 0) continue;
+        float a = half_area(s[i].box);
+        if (!(a <= best)) {  // NaN / inf areas (degenerate boxes) still get picked
+          best = a;
+          pick = i;
+        }
+      }
+      if (pick < 0) break;
+      Slot l, r;
+      children_of(in.nodes[s[pick].ref], l, r);
+      s[pick] = l;
+      s[n++] = r;
+    }
+    int32_t me = (int32_t)out.nodes.size();
+    out.nodes.emplace_back();
+    uint32_t deepest = 0;
+    int32_t refs[4];
+    for (int i = 0; i < n; ++i) {
+      uint32_t sub = 0;
+      refs[i] = convert(s[i].ref, &sub);
+      deepest = std::max(deepest, sub);
+    }
+    WideNode &w = out.nodes[me];
+    for (int i = 0; i < 4; ++i) {
+      for (int k = 0; k < 3; ++k) {
+        w.plane[k][i] = i < n ? s[i].box.mn[k] : 0.0f;
+        w.plane[3 + k][i] = i < n ? s[i].box.mx[k] : 0.0f;
+      }
+      w.child[i] = i < n ? refs[i] : kEmptyChild;
+      w.pad[i] = 0;
+    }
+    *need = (uint32_t)(n - 1) + deepest;  // the siblings wait on the stack while the first child is walked
+    return me;
+  }
+};
+
+}  // namespace
+
+WideBvh collapse_bvh4(const BuiltBvh &bvh) {
+  Collapser c{bvh, {}};
+  c.out.root = c.convert(bvh.root, &c.out.stack_need);
+  return std::move(c.out);
+}
+
 }  // namespace rpt

@@ -38,4 +38,26 @@ BuiltBvh build_bvh(const std::vector<Box> &shapes);
 // reference-order tree above is still built, but only to number the shapes for tie-breaking.
 BuiltBvh build_bvh_sah(const std::vector<Box> &shapes);
 
+// Four-wide form of a built tree for the device's wide traversal (rpt_device.cuh TravT<true>): 128 bytes per node, laid out
+// as the kernel reads it — rows [min x, min y, min z, max x, max y, max z][child], then the four child refs (same convention as
+// HostNode; kEmptyChild marks an unused slot), then padding to one cache line.
+struct WideNode {
+  float plane[6][4];
+  int32_t child[4];
+  int32_t pad[4];
+};
+static_assert(sizeof(WideNode) == 128, "WideNode is one 128-byte line");
+constexpr int32_t kEmptyChild = INT32_MIN;  // == RPT_DONE on the device
+
+struct WideBvh {
+  std::vector<WideNode> nodes;
+  int32_t root = -1;        // child-ref of the root (a leaf ref when the tree has one shape)
+  uint32_t stack_need = 0;  // most refs the nearest-first walk can hold on its stack at once
+};
+
+// Collapses the two-wide tree: every inner node adopts its grandchildren, largest surface area first, until it has four
+// children or only leaves are left. Boxes and leaf refs are copied bit for bit, so the wide tree encloses exactly what the
+// two-wide one does.
+WideBvh collapse_bvh4(const BuiltBvh &bvh);
+
 }  // namespace rpt

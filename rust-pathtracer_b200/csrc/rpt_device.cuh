@@ -64,7 +64,7 @@ struct __align__(16) DevInstance {
   uint32_t tri_base;  // first triangle of the mesh in the global triangle arrays
   uint32_t order;     // position in the reference's flat-BVH candidate order (tie-break only)
   uint32_t has_normals;
-  uint32_t pad;
+  int32_t blas_root4;  // the same root in the four-wide tree (DevScene::nodes4)
 };
 
 struct DevTexture {
@@ -76,6 +76,9 @@ struct DevTexture {
 struct DevScene {
   // acceleration structure
   const DevNode *nodes;  // TLAS nodes first, then every BLAS
+  // Four-wide form of the same trees (RPT_BVH4=1; nullptr otherwise): 8 float4 = 128 B per node, see TravT<true>.
+  const float4 *nodes4;
+  int32_t tlas_root4;  // child-ref into nodes4 (leaf refs are the same as in the two-wide tree)
   // TLAS leaf table: .x = instance id, .y = mesh-local triangle id or RPT_NONE (whole instance),
   // .z = global triangle index, .w = the instance's candidate order. Untransformed mesh instances are
   // flattened into the TLAS triangle by triangle (exact: their local space IS world space), so the common
@@ -545,7 +548,15 @@ __device__ __forceinline__ bool tri_test_pre(float3 p0, float3 p1, float3 p2, fl
 // Instance::hit -> Mesh::hit; world/mod.rs:166, accelerator/mod.rs:86-178, lbvh.rs:172-213,
 // instance.rs:75-133, mesh.rs:314-360). Unlike the reference (F8) it prunes by the closest hit so far;
 // results are identical because pruned boxes cannot contain a closer hit. State lives in registers.
-struct Trav {
+//
+// WIDE = true walks the four-wide collapse of the same trees (DevScene::nodes4, built by rpt::collapse_bvh4). A node is 8 float4:
+// rows 0-2 the four children's box minima (x, y, z), rows 3-5 their maxima, row 6 the four child refs (RPT_DONE = empty slot),
+// row 7 padding to one 128-byte line. The near / far plane of every child along an axis is the min or the max row depending
+// only on the sign of the ray direction, so the six plane rows are fetched through three per-ray row offsets and the slab test
+// needs no min / max per box; the (up to four) children that are hit are visited nearest first. Boxes, leaves and the
+// accept() rule are those of the two-wide tree, so the result is the same hit (tests/test_gpu_parity.py::test_bvh4_*).
+template <bool WIDE>
+struct TravT {
   float3 o, d;       // world-space ray
   float3 ro, rd;     // current-space ray (instance-local inside a BLAS)
   float3 inv, oinv;  // slab-test reciprocals of the current-space ray
@@ -554,6 +565,7 @@ struct Trav {
   uint64_t best_key;
   int cur, sp, blas_base;
   uint32_t cur_inst, cur_inst_order, cur_tri_base;
+  uint32_t near_rows;  // WIDE: row of the near plane per axis, 2 bits each at bits 0 / 8 / 16 (x: 0 or 3, y: 1 or 4, z: 2 or 5)
   bool found;
   TraceHit out;
 
@@ -562,6 +574,7 @@ struct Trav {
     rd = nd;
     slab_recip(ro, rd, inv, oinv);
     tr = tri_ray_setup(rd);
+    if (WIDE) near_rows = (inv.x < 0.0f ? 3u : 0u) | (inv.y < 0.0f ? 4u : 1u) << 8 | (inv.z < 0.0f ? 5u : 2u) << 16;
   }
   __device__ __forceinline__ void init(const DevScene &S, float3 o_, float3 d_, float tmax_) {
     o = o_;
@@ -574,7 +587,7 @@ struct Trav {
     out.prim = RPT_NONE;
     sp = 0;
     blas_base = 0;
-    cur = S.tlas_root;
+    cur = WIDE ? S.tlas_root4 : S.tlas_root;
     cur_inst = RPT_NONE;
     cur_inst_order = cur_tri_base = 0;
     set_space(o, d);
@@ -616,7 +629,56 @@ struct Trav {
   __device__ __forceinline__ bool step(const DevScene &S, int *stack, int stride, TraceWork &work) {
     {
       // ---- phase 1: descend through inner nodes (inner refs are >= 0)
-      while (cur >= 0) {
+      while (WIDE && cur >= 0) {
+        RPT_STAT(work.nodes++);
+        const float4 *np = S.nodes4 + 8 * (size_t)cur;
+        const uint32_t rx = near_rows & 0xFFu, ry = (near_rows >> 8) & 0xFFu, rz = near_rows >> 16;
+        const float4 nx = __ldg(np + rx), ny = __ldg(np + ry), nz = __ldg(np + rz);
+        const float4 fx = __ldg(np + (3u - rx)), fy = __ldg(np + (5u - ry)), fz = __ldg(np + (7u - rz));
+        const int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 6));
+        // same planes, same fmaf as slab_test(); a zero direction component turns both of its planes into NaN, which fmaxf / fminf drop
+        const float lim = closest;
+#define RPT_WIDE_CHILD(c, T, R)                                                                                                          \
+  {                                                                                                                                       \
+    const float tn = fmaxf(fmaxf(fmaf(nx.c, inv.x, -oinv.x), fmaf(ny.c, inv.y, -oinv.y)), fmaxf(fmaf(nz.c, inv.z, -oinv.z), 0.0f));       \
+    const float tf = fminf(fminf(fmaf(fx.c, inv.x, -oinv.x), fmaf(fy.c, inv.y, -oinv.y)), fminf(fmaf(fz.c, inv.z, -oinv.z), lim)) * 1.000001f; \
+    T = (tn <= tf && ch.c != RPT_DONE) ? fminf(tn, 3.402823466e38f) : RPT_INF;                                                                                   \
+    R = ch.c;                                                                                                                             \
+  }
+        float t0, t1, t2, t3;
+        int r0, r1, r2, r3;
+        RPT_WIDE_CHILD(x, t0, r0)
+        RPT_WIDE_CHILD(y, t1, r1)
+        RPT_WIDE_CHILD(z, t2, r2)
+        RPT_WIDE_CHILD(w, t3, r3)
+#undef RPT_WIDE_CHILD
+        // sort the four (t, ref) pairs by t: misses (t = +inf; a hit's t is clamped to FLT_MAX) end up last
+#define RPT_WIDE_CSWAP(ta, ra, tb, rb)    \
+  {                                       \
+    const bool sw = tb < ta;              \
+    const float tlo = sw ? tb : ta;       \
+    const int rlo = sw ? rb : ra;         \
+    tb = sw ? ta : tb;                    \
+    rb = sw ? ra : rb;                    \
+    ta = tlo;                             \
+    ra = rlo;                             \
+  }
+        RPT_WIDE_CSWAP(t0, r0, t1, r1)
+        RPT_WIDE_CSWAP(t2, r2, t3, r3)
+        RPT_WIDE_CSWAP(t0, r0, t2, r2)
+        RPT_WIDE_CSWAP(t1, r1, t3, r3)
+        RPT_WIDE_CSWAP(t1, r1, t2, r2)
+#undef RPT_WIDE_CSWAP
+        if (t0 == RPT_INF) {
+          cur = pop(stack, stride);
+        } else {
+          if (t3 != RPT_INF) stack[(sp++) * stride] = r3;
+          if (t2 != RPT_INF) stack[(sp++) * stride] = r2;
+          if (t1 != RPT_INF) stack[(sp++) * stride] = r1;
+          cur = r0;
+        }
+      }
+      while (!WIDE && cur >= 0) {
         RPT_STAT(work.nodes++);
         const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
         float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
@@ -670,7 +732,7 @@ struct Trav {
             cur_inst = hit_inst;
             cur_inst_order = inst_order;
             cur_tri_base = I.tri_base;
-            next = I.blas_root;
+            next = WIDE ? I.blas_root4 : I.blas_root;
             have_next = true;
           } else {
             float t;
@@ -702,10 +764,12 @@ struct Trav {
   }
 };
 
-template <bool ANY_HIT, bool STATS>
+using Trav = TravT<false>;
+
+template <bool ANY_HIT, bool STATS, bool WIDE = false>
 __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d, float tmax, int *stack, int stride, TraceHit &out,
                                           TraceWork &work) {
-  Trav t;
+  TravT<WIDE> t;
   t.init(S, o, d, tmax);
   t.template run<ANY_HIT, STATS>(S, stack, stride, work);
   out = t.out;

@@ -316,6 +316,9 @@ struct TileStream {
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 8  // resident CTAs per SM the traversal kernels are compiled for (register cap = 65536 / (128 * this))
 #endif
+#ifndef TRACE_MIN_BLOCKS_WIDE
+#define TRACE_MIN_BLOCKS_WIDE 6  // the four-wide walk holds seven 128-bit node rows in flight: 80 registers instead of 64
+#endif
 
 // per-thread BVH work counters -> one 64-bit atomic per warp per counter at kernel end
 __device__ __forceinline__ void flush_work(const TraceWork &w, unsigned long long *work) {
@@ -391,7 +394,10 @@ __device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t m
 // Closest-hit traversal of the path queue; appends each path to the list of its vertex's class.
 // RAYGEN: the launch of bounce 0 generates its camera vertices itself (and writes them out for the shade kernel) instead
 // of reading what a separate ray-generation kernel wrote: one 64-byte queue write + read per sample less.
-enum : int { TRAV_BVH = 0, TRAV_BVH_TMA = 1, TRAV_SMALL = 2, TRAV_BVH_REFILL = 3 };  // how the traversal kernels find hits (chosen per scene)
+enum : int { TRAV_BVH = 0, TRAV_BVH_TMA = 1, TRAV_SMALL = 2, TRAV_BVH_REFILL = 3, TRAV_BVH4 = 4 };  // how the traversal kernels find hits (chosen per scene)
+
+// TRAV_BVH4 (RPT_BVH4=1): the same trees collapsed to four children per node (rpt::collapse_bvh4, TravT<true>): half the
+// dependent node fetches per ray, one 128-byte line per node, no per-box min / max.
 
 // TRAV_BVH_REFILL (opt-in, RPT_REFILL=1): lanes whose ray has finished are re-armed with the next ray of the queue while the
 // other lanes of the warp are still walking ("persistent threads with dynamic fetch", Aila & Laine 2009), once at least
@@ -410,7 +416,7 @@ __device__ __forceinline__ void stage_small_tris(const DevScene &S, float4 *s_tr
 }
 
 template <int MODE, bool RAYGEN, bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
+__global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WIDE : TRACE_MIN_BLOCKS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
                                                          uint32_t *__restrict__ q_miss, uint32_t *__restrict__ q_diffuse,
                                                          uint32_t *__restrict__ q_ggx, uint32_t *__restrict__ counts,
                                                          unsigned long long *__restrict__ work, float *__restrict__ acc,
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DevSc
       hit = sv.found;
       th = sv.out;
     } else if (active) {
-      hit = trace_ray<false, STATS>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+      hit = trace_ray<false, STATS, MODE == TRAV_BVH4>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
     }
     if (active) {
       HitRec h;
@@ -1357,11 +1363,12 @@ __device__ __forceinline__ void shadow_light_contribution(const DevScene &S, flo
 // NEE visibility. Light samples: closest hit, accepted when ANY light-material surface is hit, whose own
 // emission is used (pt.rs:177-218, F9). Environment samples: any hit kills the sample (pt.rs:254-263).
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
+__global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WIDE : TRACE_MIN_BLOCKS) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
                                                           const uint32_t *__restrict__ sh_c, uint32_t *__restrict__ counts,
                                                           float *__restrict__ acc, unsigned long long *__restrict__ work) {
   extern __shared__ int s_stack[];
   constexpr bool SMALL = MODE == TRAV_SMALL;
+  constexpr bool WIDE = MODE == TRAV_BVH4;
   const float4 *s_tris = reinterpret_cast<const float4 *>(s_stack);
   if (SMALL) stage_small_tris(S, reinterpret_cast<float4 *>(s_stack));
   TraceWork tw{0, 0, 0};
@@ -1426,7 +1433,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
       return;
     }
     if (env_ray) {
-      if (!trace_ray<true, STATS>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) atomicAdd(acc + slot, pre);
+      if (!trace_ray<true, STATS, WIDE>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) atomicAdd(acc + slot, pre);
       return;
     }
     bool lit;
@@ -1437,7 +1444,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
       uint64_t key_l = 0;
       uint32_t inst_l = RPT_NONE;
       if (!shadow_closest_light<STATS>(S, o, d, tl, key_l, inst_l, tw)) return;  // no light along the ray: nothing to add
-      Trav tv;
+      TravT<WIDE> tv;
       tv.init(S, o, d, RPT_INF);
       tv.closest = tl;  // only geometry that beats the light (closer, or equal t with a winning tie key) is accepted
       tv.best_key = key_l;
@@ -1448,7 +1455,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow(DevS
       th.inst = inst_l;
       th.prim = 0;
     } else {
-      lit = trace_ray<false, STATS>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+      lit = trace_ray<false, STATS, WIDE>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
     }
     if (lit) shadow_light_contribution(S, o, d, th, pre, lambda, slot, acc);
   };
@@ -1854,7 +1861,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32
       sv.template run<false, false>(S, reinterpret_cast<const float4 *>(s_stack), ro, rd, tm, active, tw);
       th = sv.out;
     } else if (active) {
-      trace_ray<false, false>(S, ro, rd, tm, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+      trace_ray<false, false, MODE == TRAV_BVH4>(S, ro, rd, tm, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
     }
     if (active) {
       HitRec h;
@@ -2238,6 +2245,8 @@ void launch_trace(RptScene *S, const WaveBuffers &w, cudaStream_t st, bool stats
     if (stats) RPT_TRACE_LAUNCH(TRAV_SMALL, true); else RPT_TRACE_LAUNCH(TRAV_SMALL, false);
   } else if (S->trav_mode == TRAV_BVH_REFILL) {
     if (stats) RPT_TRACE_LAUNCH(TRAV_BVH_REFILL, true); else RPT_TRACE_LAUNCH(TRAV_BVH_REFILL, false);
+  } else if (S->trav_mode == TRAV_BVH4) {
+    if (stats) RPT_TRACE_LAUNCH(TRAV_BVH4, true); else RPT_TRACE_LAUNCH(TRAV_BVH4, false);
   } else {
     if (stats) RPT_TRACE_LAUNCH(TRAV_BVH, true); else RPT_TRACE_LAUNCH(TRAV_BVH, false);
   }
@@ -2257,6 +2266,8 @@ void launch_shadow(RptScene *S, const WaveBuffers &w, cudaStream_t st, bool stat
     if (stats) RPT_SHADOW_LAUNCH(TRAV_SMALL, true); else RPT_SHADOW_LAUNCH(TRAV_SMALL, false);
   } else if (S->trav_mode == TRAV_BVH_REFILL) {
     if (stats) RPT_SHADOW_LAUNCH(TRAV_BVH_REFILL, true); else RPT_SHADOW_LAUNCH(TRAV_BVH_REFILL, false);
+  } else if (S->trav_mode == TRAV_BVH4) {
+    if (stats) RPT_SHADOW_LAUNCH(TRAV_BVH4, true); else RPT_SHADOW_LAUNCH(TRAV_BVH4, false);
   } else {
     if (stats) RPT_SHADOW_LAUNCH(TRAV_BVH, true); else RPT_SHADOW_LAUNCH(TRAV_BVH, false);
   }
@@ -2645,7 +2656,14 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     rpt::Box box;
     bool has_normals;
     uint32_t depth;
+    uint32_t wide_need = 0;
   };
+  // Four-wide trees (TRAV_BVH4) are opt-in: RPT_BVH4=1.
+  const bool want_bvh4 = [] {
+    const char *e = std::getenv("RPT_BVH4");
+    return e && e[0] == '1';
+  }();
+  std::vector<rpt::WideBvh> blas_wide(d->num_meshes);
   std::vector<MeshInfo> minfo(d->num_meshes);
   std::vector<std::vector<DevNode>> blas_nodes(d->num_meshes);
   bool any_normals = false;
@@ -2678,6 +2696,10 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     max_blas_depth = std::max(max_blas_depth, bvh.max_depth);
     blas_nodes[m].reserve(bvh.nodes.size());
     for (auto &hn : bvh.nodes) blas_nodes[m].push_back(to_dev_node(hn, 0));
+    if (want_bvh4) {
+      blas_wide[m] = rpt::collapse_bvh4(bvh);
+      minfo[m].wide_need = blas_wide[m].stack_need;
+    }
     for (uint32_t t = 0; t < M.num_faces; ++t) {
       uint32_t mat = M.face_material ? M.face_material[t] : RPT_MAT_PACK(RPT_MAT_TAG_MATERIAL, 0);
       for (int k = 0; k < 3; ++k) {
@@ -2774,6 +2796,15 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     if (d->instances[i].kind == RPT_AGG_MESH && !flattened[i]) needed_blas_depth = std::max(needed_blas_depth, minfo[d->instances[i].mesh].depth);
   // one push per inner node on the path; shared-memory stack sized to the scene (16 / 32 / 64 / 128 entries per thread)
   uint32_t need = tlas.max_depth + needed_blas_depth + 2;
+  rpt::WideBvh tlas_wide;
+  if (want_bvh4) {
+    tlas_wide = rpt::collapse_bvh4(tlas);
+    uint32_t blas_need = 0;
+    for (uint32_t i = 0; i < d->num_instances; ++i)
+      if (d->instances[i].kind == RPT_AGG_MESH && !flattened[i]) blas_need = std::max(blas_need, minfo[d->instances[i].mesh].wide_need);
+    need = tlas_wide.stack_need + blas_need + 2;
+    S->trav_mode = TRAV_BVH4;
+  }
   S->dev.min_grab = (leaf_box.size() <= 8 && needed_blas_depth == 0) ? 4u : 1u;
   S->stack_entries = need <= 16 ? 16 : (need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 0)));
   if (S->stack_entries == 0) return bail(fail("BVH deeper than the largest traversal stack (128 entries)"));
@@ -2830,6 +2861,20 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     mesh_root[m] = minfo[m].root >= 0 ? minfo[m].root + off : minfo[m].root;
   }
 
+  std::vector<rpt::WideNode> nodes4;
+  std::vector<int32_t> mesh_root4(d->num_meshes, 0);
+  if (S->trav_mode == TRAV_BVH4) {
+    nodes4 = tlas_wide.nodes;
+    for (uint32_t m = 0; m < d->num_meshes; ++m) {
+      const int32_t off = (int32_t)nodes4.size();
+      for (rpt::WideNode n : blas_wide[m].nodes) {
+        for (int k = 0; k < 4; ++k)
+          if (n.child[k] >= 0) n.child[k] += off;
+        nodes4.push_back(n);
+      }
+      mesh_root4[m] = blas_wide[m].root >= 0 ? blas_wide[m].root + off : blas_wide[m].root;
+    }
+  }
   std::vector<DevInstance> insts(d->num_instances);
   for (uint32_t i = 0; i < d->num_instances; ++i) {
     const RptInstance &I = d->instances[i];
@@ -2844,6 +2889,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     D.order = ref_tlas.order[i];
     if (I.kind == RPT_AGG_MESH) {
       D.blas_root = mesh_root[I.mesh];
+      D.blas_root4 = mesh_root4[I.mesh];
       D.tri_base = minfo[I.mesh].tri_base;
       D.has_normals = minfo[I.mesh].has_normals;
     }
@@ -2881,6 +2927,12 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   DeviceBuffers &B = S->bufs;
   int rc = 0;
   rc |= B.upload(nodes.data(), nodes.size(), &D.nodes);
+  {
+    const rpt::WideNode *dn4 = nullptr;
+    rc |= B.upload(nodes4.data(), nodes4.size(), &dn4);
+    D.nodes4 = reinterpret_cast<const float4 *>(dn4);
+    D.tlas_root4 = tlas_wide.root;
+  }
   rc |= B.upload(insts.data(), insts.size(), &D.instances);
   rc |= B.upload(leaves.data(), leaves.size(), &D.tlas_leaves);
   rc |= B.upload(tri_verts.data(), tri_verts.size(), &D.tri_verts);
@@ -3009,6 +3061,13 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     cudaFuncSetAttribute(k_shadow<TRAV_BVH_REFILL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     cudaFuncSetAttribute(k_shadow<TRAV_BVH_REFILL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     cudaFuncSetAttribute(k_trace_rays<TRAV_BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_shadow<TRAV_BVH4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_shadow<TRAV_BVH4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace_rays<TRAV_BVH4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   }
   if (S->trav_mode == TRAV_SMALL) {
     S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_SMALL, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
@@ -3016,6 +3075,9 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   } else if (S->trav_mode == TRAV_BVH_REFILL) {
     S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH_REFILL, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
     S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH_REFILL, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+  } else if (S->trav_mode == TRAV_BVH4) {
+    S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH4, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+    S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH4, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
   } else if (S->trav_mode == TRAV_BVH_TMA) {
     S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH_TMA, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
     S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
@@ -3122,6 +3184,8 @@ int rpt_trace_rays(RptScene *S, uint32_t n, const float *origins, const float *d
   CUDA_TRY(cudaMemcpyAsync(d_t, tmax, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
   if (S->trav_mode == TRAV_SMALL)
     k_trace_rays<TRAV_SMALL><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
+  else if (S->trav_mode == TRAV_BVH4)
+    k_trace_rays<TRAV_BVH4><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
   else
     k_trace_rays<TRAV_BVH><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
   std::vector<HitRec> h(n);

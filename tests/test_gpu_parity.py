@@ -526,6 +526,45 @@ def test_lane_refill_mode_equals_tile_mode(monkeypatch, name):
     refill.close()
 
 
+@pytest.mark.parametrize("name", ["cornell", "gem", "instanced_monkeys", "kitchen_sink", "hdri2", "sun_test", "furnace", "test_nee_sphere"])
+def test_bvh4_mode_equals_bvh2(monkeypatch, name):
+    """TRAV_BVH4 (RPT_BVH4=1: the same trees collapsed to four children per node, nearest-first walk, TravT<true>) answers the
+    same queries as the two-wide walk: same hit ids (rendered primaries, random and axis-aligned rays through rpt_trace_rays),
+    same counters, same film up to the order of the energy atomics; it visits fewer nodes."""
+    world, st, flat = parity.load_scene(name, 192, 108, 4)
+    monkeypatch.setenv("RPT_BVH4", "0")
+    two = parity.cuda_scene(flat)
+    monkeypatch.setenv("RPT_BVH4", "1")
+    four = parity.cuda_scene(flat)
+    monkeypatch.delenv("RPT_BVH4")
+    p = st.params(seed=29, flags=2)
+    f2, c2 = two.render_pt(p)
+    f4, c4 = four.render_pt(p)
+    for k in ("segments", "bounce_rays", "shadow_rays", "shadow_rays_traced", "env_hits", "nee_vertices"):
+        assert getattr(c2, k) == getattr(c4, k), (name, k, getattr(c2, k), getattr(c4, k))
+    assert c4.walk_nodes < c2.walk_nodes or c2.walk_nodes == 0, (name, c2.walk_nodes, c4.walk_nodes)
+    ok = np.isfinite(f2)
+    assert np.array_equal(ok, np.isfinite(f4))
+    assert np.allclose(f2[ok], f4[ok], rtol=1e-5, atol=1e-9), (name, float(np.abs(f2[ok] - f4[ok]).max()))
+    a = two.trace_primary(p)
+    b = four.trace_primary(p)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    rng = np.random.default_rng(5)
+    scale = {"instanced_monkeys": 40.0, "kitchen_sink": 3.0}.get(name, 1.0)
+    lo, hi = (-0.9 * scale, 0.9 * scale) if name != "cornell" else (0.01, 0.54)
+    o1 = rng.uniform(lo, hi, size=(12000, 3)).astype(np.float32)
+    d1 = rng.normal(size=(12000, 3)).astype(np.float32)
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    o2, d2 = axis_aligned_rays(rng, 6000, lo, hi)
+    o, d = np.concatenate([o1, o2]), np.concatenate([d1, d2])
+    tmax = np.full(len(o), np.inf, np.float32)
+    a = two.trace_rays(o, d, tmax)
+    b = four.trace_rays(o, d, tmax)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    two.close()
+    four.close()
+
+
 @pytest.mark.parametrize("name", ["cornell", "kitchen_sink", "hdri2"])
 def test_two_stream_half_waves_equal_single_stream(monkeypatch, name):
     """RPT_OVERLAP=1 (a wave cut into two half-waves on two streams; opt-in after measurement, profiles/r02_overlap.md) renders

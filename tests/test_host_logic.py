@@ -321,6 +321,19 @@ def test_oracle_closest_hits_against_brute_force(pkg):
     assert np.allclose(ot[both], best_t[both], rtol=1e-5, atol=1e-6)
 
 
+def test_bvh4_collapse_encloses_what_the_binary_tree_does(tmp_path):
+    """rpt::collapse_bvh4 (the four-wide trees of TRAV_BVH4): tests/cpp/bvh4_check.cpp builds both of the library's binary trees
+    over random boxes (1 .. 20000 shapes), collapses them and checks that every leaf appears once with its own box, that
+    un-pruned walks of both trees reach the same leaves for random and axis-aligned rays, and that the nearest-first walk stays
+    within WideBvh::stack_need (what rpt_scene_create sizes the traversal stack with)."""
+    exe = tmp_path / "bvh4_check"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "cpp", "bvh4_check.cpp"),
+                    os.path.join(ROOT, "rust-pathtracer_b200", "csrc", "rpt_bvh.cpp")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("fails=0") == 18, out.stdout
+
+
 def test_exr_writer_roundtrip(pkg, tmp_path):
     """output_film's EXR payload (tonemap/mod.rs:225-247): the writer's file is read back by the package's own reader and,
     when OpenCV was built with OpenEXR, by an independent decoder."""
