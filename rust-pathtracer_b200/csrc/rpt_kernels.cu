@@ -78,7 +78,7 @@ enum : uint32_t {
   F_TRACE = 12, F_SHADOW = 13, F_SHADE_DIFFUSE = 14, F_SHADE_GGX = 15,  // claim counters of the dynamic tile hand-out (TileStream)
   Q_NEE_DIFFUSE = 16, Q_NEE_GGX = 17,  // sizes of the two NEE hand-over queues (split shade pipeline), padding included
   N_NEE = 18,                          // valid NEE hand-over records (both classes)
-  F_NEE_DIFFUSE = 19, F_NEE_GGX = 20,
+  F_NEE_DIFFUSE = 19, F_NEE_GGX = 20, F_NEE_DIFFUSE_ENV = 21, F_NEE_GGX_ENV = 22,
   Q_COUNT = 24
 };
 
@@ -1170,11 +1170,32 @@ __global__ void __launch_bounds__(SHADE_THREADS, VERTEX_MIN_BLOCKS) k_shade_vert
 #define NEE_CHUNK 128u
 #endif
 #define NEE_BINS (NEE_GRID * NEE_GRID * NEE_GRID)
-template <uint32_t CLASS>
+// KIND (scenes that sample BOTH the environment and lights, 0 < p_env < 1): which of the two a sample draws is a per-sample
+// coin flip (pt.rs:350-353), so a warp that walks "lane = vertex, loop over its L samples" (NEE_BOTH) runs the environment
+// branch (two CDF searches + the f64 uv <-> direction round trips) and the light branch with half its lanes each: ncu shows
+// 15.9 lanes per instruction on the GGX + HDR scene. There the queue is walked by TWO launches, NEE_LIGHT then NEE_ENV: each
+// classifies every (vertex, sample) pair (one Philox draw), parks the pairs of ITS kind in a per-warp ring buffer, and draws
+// them 32 at a time, one per lane, all lanes in the same branch. An item re-reads its 64-byte vertex record (L1 / L2 hit) and
+// repeats the Philox draw. One kind per launch rather than two rings in one launch: the single-launch form does reach 27-29
+// lanes, but its warps sit in different halves of 90 KB of code and wait for instructions (no-instruction stalls 5-11 warps
+// per issue, profiles/r02_nee_sort_*); a launch that compiles only one branch halves the footprint.
+// Samples are the same samples; only the order of the shadow records (and of the energy atomics behind them) changes.
+enum : int { NEE_BOTH = 0, NEE_LIGHT = 1, NEE_ENV = 2 };
+#define NEE_RING 64u
+struct NeeVertex {
+  float3 p, nrm, wi;
+  float beta, lambda, albedo;
+  uint32_t slot, pixel, sample;
+  Frame frame;
+  GgxParams gp;
+};
+template <uint32_t CLASS, int KIND>
 __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx R, uint32_t bounce, const NeeRec *__restrict__ nee,
                                                          uint32_t *__restrict__ counts, float4 *__restrict__ sh_a, float4 *__restrict__ sh_b,
                                                          uint32_t *__restrict__ sh_c) {
   __shared__ WarpChunk s_chunks[SHADE_THREADS / 32][NEE_BINS];
+  constexpr bool SORTED = KIND != NEE_BOTH;
+  __shared__ uint2 s_ring[SORTED ? SHADE_THREADS / 32 : 1][SORTED ? NEE_RING : 1];  // (record, sample index) per parked item
   WarpChunk *st_shadow = s_chunks[threadIdx.x >> 5];
   const uint32_t n = counts[CLASS == Q_DIFFUSE ? Q_NEE_DIFFUSE : Q_NEE_GGX];
   const uint32_t bc = n >= BIN_MIN_ITEMS ? NEE_CHUNK : QCHUNK_BINNED_SMALL;
@@ -1187,110 +1208,176 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
   uint32_t n_shadow = 0, n_sh_ref = 0;
   auto mark_shadow = [&](uint32_t e) { sh_c[e] = RPT_NONE; };
   const float inv_l = 1.0f / (float)L;
-  TileStream ts;
-  ts.init(counts + (CLASS == Q_DIFFUSE ? F_NEE_DIFFUSE : F_NEE_GGX), n_tiles, gridDim.x * (SHADE_THREADS / 32), S.min_grab);
-  for (uint32_t tile = ts.next(); tile != RPT_NONE; tile = ts.next()) {
-    const uint32_t i = tile * 32u + lane;
-    bool do_nee = i < n;
+
+  // the hand-over record of vertex i; returns false for chunk padding (and for lanes without a record)
+  auto load_vertex = [&](uint32_t i, bool act, NeeVertex &v) -> bool {
     float4 r0 = make_float4(0, 0, 0, 0), r1 = make_float4(0, 0, 1, 0), r2 = make_float4(0, 0, 1, 0), r3 = make_float4(0, 0, 0, 0);
-    if (do_nee) {
+    if (act) {
       const float4 *rp = reinterpret_cast<const float4 *>(nee + i);
       r2 = __ldg(rp + 2);
-      do_nee = __float_as_uint(r2.w) != RPT_NONE;  // chunk padding
-      if (do_nee) {
+      act = __float_as_uint(r2.w) != RPT_NONE;  // chunk padding
+      if (act) {
         r0 = __ldg(rp);
         r1 = __ldg(rp + 1);
         r3 = __ldg(rp + 3);
       }
     }
-    const float3 p = f3(r0), nrm = f3(r1), wi_nee = f3(r2);
-    const float beta = r0.w, lambda = r1.w;
-    const uint32_t slot = __float_as_uint(r2.w);
-    const uint32_t pixel = slot % R.wh, sample = R.sample_base + slot / R.wh;
-    const Frame frame = frame_from_normal(nrm);
-    GgxParams gp;
-    gp.alpha = 1.0f;
-    gp.eta_inner = r3.x;
-    gp.eta_outer = r3.y;
-    gp.kappa = r3.z;
-    gp.metallic = false;
-    if (CLASS == Q_GGX && do_nee) {
+    v.p = f3(r0);
+    v.nrm = f3(r1);
+    v.wi = f3(r2);
+    v.beta = r0.w;
+    v.lambda = r1.w;
+    v.slot = __float_as_uint(r2.w);
+    v.pixel = v.slot % R.wh;
+    v.sample = R.sample_base + v.slot / R.wh;
+    v.frame = frame_from_normal(v.nrm);
+    v.gp.alpha = 1.0f;
+    v.gp.eta_inner = r3.x;
+    v.gp.eta_outer = r3.y;
+    v.gp.kappa = r3.z;
+    v.gp.metallic = false;
+    if (CLASS == Q_GGX && act) {
       const RptMaterial &m = S.materials[__float_as_uint(r3.w)];
-      gp.alpha = m.alpha;
-      gp.metallic = m.metallic != 0;
+      v.gp.alpha = m.alpha;
+      v.gp.metallic = m.metallic != 0;
     }
-    const float albedo = r3.x;
-    for (uint32_t ls = 0; ls < L; ++ls) {
-      bool has = false;
-      float4 a = make_float4(0, 0, 0, 0), b4 = make_float4(0, 0, 0, 0);
-      uint32_t c = 0;
-      if (do_nee) {
-        RptRand4 sn = rpt_philox(R.seed, pixel, sample, rpt_block_nee(bounce, L, ls));
-        float pick;
-        bool sample_world = choose(sn.x, S.p_env, pick);  // pt.rs:350-353
-        float3 dir = f3(0, 0, 1);
-        float light_pdf = 0.0f, emission = 1.0f;
-        bool valid = true;
-        if (sample_world) {
-          float eu, ev;
-          env_sample_uv(S, sn.y, sn.z, eu, ev, light_pdf);
-          dir = uv_to_direction(eu, ev);
-          emission = env_emission(S, eu, ev, lambda);
-        } else {
-          valid = S.num_lights > 0;
-          if (valid) {
-            uint32_t li = (uint32_t)clampf((float)S.num_lights * pick, 0.0f, (float)S.num_lights - 1.0f);  // world/mod.rs:109
-            instance_sample(S.instances[S.lights[li]], sn.y, sn.z, p, dir, light_pdf);
-            light_pdf = light_pdf * (1.0f / (float)S.num_lights);
-            valid = light_pdf != 0.0f;  // pt.rs:151-153
-          }
-        }
-        float3 local_wo = to_local(frame, dir);
-        if (sample_world && local_wo.z <= 0.0f) valid = false;  // pt.rs:245-247
+    v.albedo = r3.x;
+    return act;
+  };
+  // sample ls of vertex v -> at most one shadow record. All 32 lanes must call (the append is warp-collective).
+  auto draw_sample = [&](const NeeVertex &v, bool do_nee, uint32_t ls) {
+    bool has = false;
+    float4 a = make_float4(0, 0, 0, 0), b4 = make_float4(0, 0, 0, 0);
+    uint32_t c = 0;
+    if (do_nee) {
+      RptRand4 sn = rpt_philox(R.seed, v.pixel, v.sample, rpt_block_nee(bounce, L, ls));
+      float pick;
+      bool sample_world = choose(sn.x, S.p_env, pick);  // pt.rs:350-353
+      if (KIND == NEE_LIGHT) sample_world = false;  // (what the classification found; lets the compiler drop the other branch)
+      if (KIND == NEE_ENV) sample_world = true;
+      float3 dir = f3(0, 0, 1);
+      float light_pdf = 0.0f, emission = 1.0f;
+      bool valid = true;
+      if (sample_world) {
+        float eu, ev;
+        env_sample_uv(S, sn.y, sn.z, eu, ev, light_pdf);
+        dir = uv_to_direction(eu, ev);
+        emission = env_emission(S, eu, ev, v.lambda);
+      } else {
+        valid = S.num_lights > 0;
         if (valid) {
-          Bsdf bs;
-          if (CLASS == Q_GGX) {
-            bs = ggx_bsdf(gp, wi_nee, local_wo);
-          } else {  // lambertian.rs:16-32 / diffuse_light.rs:29-45
-            bool same = local_wo.z * wi_nee.z > 0.0f;
-            bs.f = same ? albedo / RPT_PI : 0.0f;
-            bs.pdf = same ? fabsf(local_wo.z) / RPT_PI : 0.0f;
-          }
-          n_sh_ref++;  // the reference traces (and counts) this ray whatever its weight
-          float weight = R.only_direct ? 1.0f : power_heuristic_generic(light_pdf, bs.pdf);
-          float pre;
-          float3 so;
-          if (sample_world) {
-            pre = beta * weight * bs.f * emission * fabsf(local_wo.z) * (1.0f / light_pdf) * inv_l;  // pt.rs:313-318
-            so = p + (nrm * RPT_NORMAL_OFFSET) * signumf(dir.z);  // WORLD z (quirk Q12, pt.rs:256)
-            c = slot | 0x80000000u;
-          } else {
-            pre = bs.f * beta * fabsf(local_wo.z) * weight / light_pdf * inv_l;  // pt.rs:196-202 minus the light-side terms
-            so = p + (nrm * RPT_NORMAL_OFFSET) * signumf(local_wo.z);  // pt.rs:171-174
-            c = slot;
-          }
-          if (pre != 0.0f) {  // a zero pre-factor cannot contribute: skip the visibility query
-            has = true;
-            a = make_float4(so.x, so.y, so.z, pre);
-            b4 = make_float4(dir.x, dir.y, dir.z, lambda);
-          }
+          uint32_t li = (uint32_t)clampf((float)S.num_lights * pick, 0.0f, (float)S.num_lights - 1.0f);  // world/mod.rs:109
+          instance_sample(S.instances[S.lights[li]], sn.y, sn.z, v.p, dir, light_pdf);
+          light_pdf = light_pdf * (1.0f / (float)S.num_lights);
+          valid = light_pdf != 0.0f;  // pt.rs:151-153
         }
       }
-      uint32_t bin_sh = 0u;
-      if (nbins > 1) {  // origin cell
-        const float g = (float)NEE_GRID;
-        uint32_t cx = (uint32_t)fminf(fmaxf((a.x - S.world_min.x) * S.world_inv_extent.x * g, 0.0f), g - 1.0f);
-        uint32_t cy = (uint32_t)fminf(fmaxf((a.y - S.world_min.y) * S.world_inv_extent.y * g, 0.0f), g - 1.0f);
-        uint32_t cz = (uint32_t)fminf(fmaxf((a.z - S.world_min.z) * S.world_inv_extent.z * g, 0.0f), g - 1.0f);
-        bin_sh = (cz * NEE_GRID + cy) * NEE_GRID + cx;
+      float3 local_wo = to_local(v.frame, dir);
+      if (sample_world && local_wo.z <= 0.0f) valid = false;  // pt.rs:245-247
+      if (valid) {
+        Bsdf bs;
+        if (CLASS == Q_GGX) {
+          bs = ggx_bsdf(v.gp, v.wi, local_wo);
+        } else {  // lambertian.rs:16-32 / diffuse_light.rs:29-45
+          bool same = local_wo.z * v.wi.z > 0.0f;
+          bs.f = same ? v.albedo / RPT_PI : 0.0f;
+          bs.pdf = same ? fabsf(local_wo.z) / RPT_PI : 0.0f;
+        }
+        n_sh_ref++;  // the reference traces (and counts) this ray whatever its weight
+        float weight = R.only_direct ? 1.0f : power_heuristic_generic(light_pdf, bs.pdf);
+        float pre;
+        float3 so;
+        if (sample_world) {
+          pre = v.beta * weight * bs.f * emission * fabsf(local_wo.z) * (1.0f / light_pdf) * inv_l;  // pt.rs:313-318
+          so = v.p + (v.nrm * RPT_NORMAL_OFFSET) * signumf(dir.z);  // WORLD z (quirk Q12, pt.rs:256)
+          c = v.slot | 0x80000000u;
+        } else {
+          pre = bs.f * v.beta * fabsf(local_wo.z) * weight / light_pdf * inv_l;  // pt.rs:196-202 minus the light-side terms
+          so = v.p + (v.nrm * RPT_NORMAL_OFFSET) * signumf(local_wo.z);  // pt.rs:171-174
+          c = v.slot;
+        }
+        if (pre != 0.0f) {  // a zero pre-factor cannot contribute: skip the visibility query
+          has = true;
+          a = make_float4(so.x, so.y, so.z, pre);
+          b4 = make_float4(dir.x, dir.y, dir.z, v.lambda);
+        }
       }
-      uint32_t q = chunk_append_binned(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow, bc);
-      if (has) {
-        sh_a[q] = a;
-        sh_b[q] = b4;
-        sh_c[q] = c;
+    }
+    uint32_t bin_sh = 0u;
+    if (nbins > 1) {  // origin cell
+      const float g = (float)NEE_GRID;
+      uint32_t cx = (uint32_t)fminf(fmaxf((a.x - S.world_min.x) * S.world_inv_extent.x * g, 0.0f), g - 1.0f);
+      uint32_t cy = (uint32_t)fminf(fmaxf((a.y - S.world_min.y) * S.world_inv_extent.y * g, 0.0f), g - 1.0f);
+      uint32_t cz = (uint32_t)fminf(fmaxf((a.z - S.world_min.z) * S.world_inv_extent.z * g, 0.0f), g - 1.0f);
+      bin_sh = (cz * NEE_GRID + cy) * NEE_GRID + cx;
+    }
+    uint32_t q = chunk_append_binned(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow, bc);
+    if (has) {
+      sh_a[q] = a;
+      sh_b[q] = b4;
+      sh_c[q] = c;
+    }
+    n_shadow += has;
+  };
+
+  TileStream ts;
+  ts.init(counts + (KIND == NEE_ENV ? (CLASS == Q_DIFFUSE ? F_NEE_DIFFUSE_ENV : F_NEE_GGX_ENV) : (CLASS == Q_DIFFUSE ? F_NEE_DIFFUSE : F_NEE_GGX)), n_tiles,
+          gridDim.x * (SHADE_THREADS / 32), S.min_grab);
+  if constexpr (!SORTED) {
+    for (uint32_t tile = ts.next(); tile != RPT_NONE; tile = ts.next()) {
+      const uint32_t i = tile * 32u + lane;
+      NeeVertex v;
+      const bool do_nee = load_vertex(i, i < n, v);
+      for (uint32_t ls = 0; ls < L; ++ls) draw_sample(v, do_nee, ls);
+    }
+  } else {
+    uint2 *ring = s_ring[threadIdx.x >> 5];
+    uint32_t head = 0u, tail = 0u;  // warp-uniform, free-running; entries live at index & (NEE_RING - 1)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // producer state: the tile being classified, one sample index per step
+    uint32_t i = 0u, ls = L, pixel = 0u, sample = 0u;
+    bool do_nee = false, more = true;
+    while (true) {
+      if (tail - head < 32u && more) {
+        // classify sample `ls` of the current tile's vertices (one Philox draw each) and park the pairs of this launch's kind
+        if (ls == L) {
+          const uint32_t tile = ts.next();
+          if (tile == RPT_NONE) {
+            more = false;
+            continue;
+          }
+          i = tile * 32u + lane;
+          uint32_t slot = RPT_NONE;
+          if (i < n) slot = __float_as_uint(__ldg(reinterpret_cast<const float4 *>(nee + i) + 2).w);
+          do_nee = slot != RPT_NONE;
+          pixel = slot % R.wh;
+          sample = R.sample_base + slot / R.wh;
+          ls = 0u;
+        }
+        bool mine = false;
+        if (do_nee) {
+          RptRand4 sn = rpt_philox(R.seed, pixel, sample, rpt_block_nee(bounce, L, ls));
+          float pick;
+          mine = choose(sn.x, S.p_env, pick) == (KIND == NEE_ENV);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+        if (mine) ring[(tail + __popc(m & lt_mask)) & (NEE_RING - 1u)] = make_uint2(i, ls);
+        tail += __popc(m);
+        ++ls;
+        __syncwarp();
+        continue;
       }
-      n_shadow += has;
+      if (tail == head) break;
+      // up to 32 parked items, one per lane, every lane in the same branch of draw_sample
+      const uint32_t cnt = min(32u, tail - head);
+      const bool act = lane < cnt;
+      uint2 item = make_uint2(0u, 0u);
+      if (act) item = ring[(head + lane) & (NEE_RING - 1u)];
+      head += cnt;
+      __syncwarp();
+      NeeVertex v;
+      const bool ok = load_vertex(item.x, act, v);
+      draw_sample(v, ok, item.y);
     }
   }
   chunk_pad_binned(st_shadow, NEE_BINS, mark_shadow, bc);
@@ -1972,6 +2059,7 @@ struct RptScene {
   uint32_t env_stack_count = 0;  // textures in the environment's stack (HDR)
   bool has_ggx = true;     // any material of the GGX class (else its shade kernel is never launched)
   bool fused_shade = false;  // RPT_FUSED_SHADE=1: the round-1 single shade kernel instead of k_shade_vertex + k_nee
+  bool mixed_nee = false;  // k_nee<., NEE_LIGHT> + k_nee<., NEE_ENV>: samples sorted by kind before they are drawn
   int trav_mode = TRAV_BVH;  // TRAV_SMALL (RPT_SMALL=1) for scenes of <= RPT_SMALL_MAX leaves without a BLAS;
                              // TRAV_BVH_TMA: k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
   size_t counts_cap = 0;     // bounces the per-bounce counter block has room for
@@ -2478,11 +2566,23 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
           }
           if (P->light_samples > 0) {
             T.begin(K_NEE_DIFFUSE);
-            k_nee<Q_DIFFUSE><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
+            if (S->mixed_nee) {
+              k_nee<Q_DIFFUSE, NEE_LIGHT><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
+              k_nee<Q_DIFFUSE, NEE_ENV><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
+              S->kernel_launches[K_NEE_DIFFUSE] += 1;  // (one timing span, two launches)
+            } else {
+              k_nee<Q_DIFFUSE, NEE_BOTH><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
+            }
             T.end();
             if (S->has_ggx) {
               T.begin(K_NEE_GGX);
-              k_nee<Q_GGX><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
+              if (S->mixed_nee) {
+                k_nee<Q_GGX, NEE_LIGHT><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
+                k_nee<Q_GGX, NEE_ENV><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
+                S->kernel_launches[K_NEE_GGX] += 1;
+              } else {
+                k_nee<Q_GGX, NEE_BOTH><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
+              }
               T.end();
             }
           }
@@ -3097,8 +3197,18 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   } else {
     S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_vertex<Q_DIFFUSE>, SHADE_THREADS, 0, S->num_sms);
     S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_vertex<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
-    S->grid[K_NEE_DIFFUSE] = occupancy_grid(k_nee<Q_DIFFUSE>, SHADE_THREADS, 0, S->num_sms);
-    S->grid[K_NEE_GGX] = occupancy_grid(k_nee<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
+    {
+      // parked (vertex, sample) items sorted by kind: only where both kinds occur (see k_nee); RPT_NEE_SORT=0 / 1 overrides
+      const char *e = std::getenv("RPT_NEE_SORT");
+      S->mixed_nee = e ? e[0] == '1' : (S->dev.p_env > 0.0f && S->dev.p_env < 1.0f);
+    }
+    if (S->mixed_nee) {  // (the two kinds share a grid size: the smaller of their occupancies)
+      S->grid[K_NEE_DIFFUSE] = std::min(occupancy_grid(k_nee<Q_DIFFUSE, NEE_LIGHT>, SHADE_THREADS, 0, S->num_sms), occupancy_grid(k_nee<Q_DIFFUSE, NEE_ENV>, SHADE_THREADS, 0, S->num_sms));
+      S->grid[K_NEE_GGX] = std::min(occupancy_grid(k_nee<Q_GGX, NEE_LIGHT>, SHADE_THREADS, 0, S->num_sms), occupancy_grid(k_nee<Q_GGX, NEE_ENV>, SHADE_THREADS, 0, S->num_sms));
+    } else {
+      S->grid[K_NEE_DIFFUSE] = occupancy_grid(k_nee<Q_DIFFUSE, NEE_BOTH>, SHADE_THREADS, 0, S->num_sms);
+      S->grid[K_NEE_GGX] = occupancy_grid(k_nee<Q_GGX, NEE_BOTH>, SHADE_THREADS, 0, S->num_sms);
+    }
   }
   S->grid[K_FILM] = occupancy_grid(k_film, 256, film_smem, S->num_sms);
   lap("occupancy queries");

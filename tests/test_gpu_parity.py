@@ -565,6 +565,30 @@ def test_bvh4_mode_equals_bvh2(monkeypatch, name):
     four.close()
 
 
+@pytest.mark.parametrize("name", ["hdri2", "kitchen_sink", "instanced_monkeys", "cornell", "sun_test", "hdri"])
+def test_nee_samples_sorted_by_kind_equal_unsorted(monkeypatch, name):
+    """k_nee<., NEE_LIGHT> + k_nee<., NEE_ENV>: in scenes that sample both the environment and lights (0 < p_env < 1) every (vertex, sample) pair is
+    classified first and the pairs are drawn 32 of a kind at a time (default there; RPT_NEE_SORT=0 / 1 forces either form).
+    The samples are the same samples: identical counters, film equal up to the order of the energy atomics."""
+    world, st, flat = parity.load_scene(name, 192, 108, 4)
+    monkeypatch.setenv("RPT_NEE_SORT", "0")
+    plain = parity.cuda_scene(flat)
+    monkeypatch.setenv("RPT_NEE_SORT", "1")
+    srt = parity.cuda_scene(flat)
+    monkeypatch.delenv("RPT_NEE_SORT")
+    p = st.params(seed=31, flags=2)
+    f0, c0 = plain.render_pt(p)
+    f1, c1 = srt.render_pt(p)
+    for k in ("segments", "bounce_rays", "shadow_rays", "shadow_rays_traced", "env_hits", "nee_vertices", "walk_nodes", "walk_tris"):
+        assert getattr(c0, k) == getattr(c1, k), (name, k, getattr(c0, k), getattr(c1, k))
+    assert c0.shadow_rays > 0
+    ok = np.isfinite(f0)
+    assert np.array_equal(ok, np.isfinite(f1))
+    assert np.allclose(f0[ok], f1[ok], rtol=1e-5, atol=1e-9), (name, float(np.abs(f0[ok] - f1[ok]).max()))
+    plain.close()
+    srt.close()
+
+
 @pytest.mark.parametrize("name", ["cornell", "kitchen_sink", "hdri2"])
 def test_two_stream_half_waves_equal_single_stream(monkeypatch, name):
     """RPT_OVERLAP=1 (a wave cut into two half-waves on two streams; opt-in after measurement, profiles/r02_overlap.md) renders
