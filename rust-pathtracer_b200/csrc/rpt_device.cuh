@@ -119,6 +119,7 @@ struct DevScene {
   float3 env_sun_dir;
   int32_t env_texstack;
   float4 env_rot_fwd[3], env_rot_rev[3];
+  uint32_t env_unrotated;  // both are the identity: the uv -> direction -> uv round trips take uv_roundtrip_unrotated_cr
   uint32_t imap_rows, imap_cols, imap_marginal_n;
   const float *imap_row_pdf, *imap_row_cdf, *imap_m_pdf, *imap_m_cdf;
   float imap_marginal_integral;
@@ -236,6 +237,58 @@ __device__ __noinline__ float3 uv_to_direction_cr(float u, float v) {
 __device__ __noinline__ float2 direction_to_uv_cr(float3 d) {
   float theta = (float)atan2((double)d.y, (double)d.x);
   float phi = (float)acos((double)d.z);
+  return make_float2(theta / 2.0f / RPT_PI + 0.5f, phi / RPT_PI);
+}
+// direction_to_uv_cr(uv_to_direction_cr(u, v)) — the round trip every HDR-environment lookup makes (environment.rs:56-98,
+// 198-258, 303-353) — for an UNROTATED environment, without the f64 atan2 / acos (27 % of the environment NEE kernel's
+// instructions on the GGX + HDR scene). The direction is the f32-rounded image of two angles whose f64 sines and cosines are
+// already at hand, so each angle of the way back is the angle of the way out plus a tiny rotation that needs no inverse
+// trigonometry:
+//   atan2(dy, dx) = a + atan2(dy cos a - dx sin a, dx cos a + dy sin a)         (|.| ~ 1e-7: atan t = t - t^3 / 3)
+//   acos(dz)      = b + atan2(w cos b - dz sin b, dz cos b + w sin b), w = sqrt((1 - dz)(1 + dz))
+// evaluated in f64 (absolute error ~3e-16, that of the libm calls it replaces), then rounded to f32 once like they are.
+// Lanes where the rotation is not tiny (poles: dz = +-1 or v within ~1e-4 of them; a degenerate azimuth) take the libm path.
+// tests/test_host_logic.py checks the identity against libm on 1.4e8 inputs (0 differing f32 results);
+// tests/test_gpu_parity.py::test_env_roundtrip_fast_path compares the two device paths through rpt_debug_env_roundtrip.
+__device__ __noinline__ float2 uv_roundtrip_unrotated_cr(float u, float v) {
+  const float a = (u - 0.5f) * RPT_TAU, b = v * RPT_PI;  // uv_to_direction_cr's own f32 angles
+  // (the polar angle first, then the azimuth: at most one pair of f64 sine / cosine is live at a time)
+  float phi, fsp, fcp;
+  {
+    double sp, cp;
+    sincos((double)b, &sp, &cp);
+    fsp = (float)sp;
+    fcp = (float)cp;
+    const double z = (double)fcp;  // direction.z
+    const double w = sqrt((1.0 - z) * (1.0 + z));
+    const double c2 = fma(z, cp, w * sp), s2 = fma(w, cp, -(z * sp));
+    const double t = s2 * (2.0 - c2);  // 1 / c2 = 2 - c2 + O((1 - c2)^2), c2 = cos(rotation) = 1 - O(1e-7)
+    if (fabs(z) != 1.0 && fabs(t) < 1e-3)
+      phi = (float)((double)b + t * (1.0 - t * t * (1.0 / 3.0)));
+    else
+      phi = (float)acos(z);
+  }
+  float theta;
+  {
+    double st, ct;
+    sincos((double)a, &st, &ct);
+    const float dx = fsp * (float)ct, dy = fsp * (float)st;  // direction.x, direction.y
+    const double x = (double)dx, y = (double)dy;
+    const double c = fma(x, ct, y * st), s = fma(y, ct, -(x * st));
+    const double t = s / (c > 1e-30 ? c : 1.0);
+    if (c > 1e-30 && fabs(t) < 1e-3) {
+      const double kPi = 3.14159265358979323846;
+      double th = (double)a + t * (1.0 - t * t * (1.0 / 3.0));
+      if (th > kPi) th -= 2.0 * kPi;
+      else if (th < -kPi) th += 2.0 * kPi;
+      theta = (float)th;
+    } else {
+      // (the poles.) The general path multiplies by the identity matrix in f32, which changes nothing but the sign of a zero
+      // component (-0 + 0 = +0) - and that sign is what atan2 decides by here.
+      const float ndx = 1.0f * dx + 0.0f * dy + 0.0f * fcp, ndy = 0.0f * dx + 1.0f * dy + 0.0f * fcp;  // xform_vec(identity, d)
+      theta = (float)atan2((double)ndy, (double)ndx);
+    }
+  }
   return make_float2(theta / 2.0f / RPT_PI + 0.5f, phi / RPT_PI);
 }
 __device__ __forceinline__ float power_heuristic(float a, float b) { return (a * a) / (a * a + b * b); }
@@ -1288,6 +1341,11 @@ __device__ __forceinline__ void nearest_cdf_sample(const float *__restrict__ pdf
 // ---------------------------------------------------------------------------------------------
 // environment (world/environment.rs)
 // ---------------------------------------------------------------------------------------------
+// uv -> direction -> rotate -> uv (the HDR environment's lookups all go through it)
+__device__ __forceinline__ float2 env_roundtrip(const DevScene &S, const float4 *rot, float u, float v) {
+  if (S.env_unrotated) return uv_roundtrip_unrotated_cr(u, v);
+  return direction_to_uv_cr(xform_vec(rot, uv_to_direction_cr(u, v)));
+}
 __device__ __forceinline__ bool env_in_sun(const DevScene &S, float u, float v) {
   float3 dir = uv_to_direction(u, v);
   float c = dot(S.env_sun_dir, dir);
@@ -1297,16 +1355,14 @@ __device__ __forceinline__ bool env_in_sun(const DevScene &S, float u, float v) 
 __device__ __forceinline__ float env_emission(const DevScene &S, float u, float v, float lambda) {  // :56-98
   if (S.env_kind == RPT_ENV_CONSTANT) return curve_eval(S, S.env_curve, lambda) * S.env_strength;
   if (S.env_kind == RPT_ENV_SUN) return env_in_sun(S, u, v) ? curve_eval(S, S.env_curve, lambda) * S.env_strength : 0.0f;
-  float3 nd = xform_vec(S.env_rot_rev, uv_to_direction_cr(u, v));
-  float2 q = direction_to_uv_cr(nd);
+  float2 q = env_roundtrip(S, S.env_rot_rev, u, v);
   return texstack_eval(S, S.env_texstack, lambda, q.x, q.y) * S.env_strength;
 }
 __device__ __forceinline__ float env_pdf_for(const DevScene &S, float u, float v) {  // :198-258
   if (S.env_kind == RPT_ENV_CONSTANT) return 1.0f / (4.0f * RPT_PI);
   if (S.env_kind == RPT_ENV_SUN) return env_in_sun(S, u, v) ? 1.0f / (2.0f * RPT_PI * (1.0f - cosf(S.env_angular_diameter))) : 0.0f;
   if (S.imap_rows == 0) return 1.0f / (4.0f * RPT_PI);
-  float3 nd = xform_vec(S.env_rot_rev, uv_to_direction_cr(u, v));
-  float2 q = direction_to_uv_cr(nd);
+  float2 q = env_roundtrip(S, S.env_rot_rev, u, v);
   float uu = q.x, vv = q.y;
   float m = nearest_curve_eval(S.imap_m_pdf, S.imap_marginal_n, uu);
   uint32_t row = (uint32_t)(clampf(uu, 0.0f, 1.0f - RPT_EPS) * (float)S.imap_rows);
@@ -1333,8 +1389,7 @@ __device__ __forceinline__ void env_sample_uv(const DevScene &S, float sx, float
   uint32_t row = (uint32_t)(uu * (float)S.imap_rows);
   if (row >= S.imap_rows) row = S.imap_rows - 1;
   nearest_cdf_sample(S.imap_row_pdf + (size_t)row * S.imap_cols, S.imap_row_cdf + (size_t)row * S.imap_cols, S.imap_cols, 1.0f, sx, vv, col_pdf);
-  float3 nw = xform_vec(S.env_rot_fwd, uv_to_direction_cr(uu, vv));
-  float2 q = direction_to_uv_cr(nw);
+  float2 q = env_roundtrip(S, S.env_rot_fwd, uu, vv);
   u = q.x;
   v = q.y;
   pdf = row_pdf * col_pdf * (2.0f * RPT_PI * RPT_PI * sinf(RPT_PI * v) + 0.001f) + 0.001f;

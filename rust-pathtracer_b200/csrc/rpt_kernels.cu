@@ -1181,6 +1181,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, VERTEX_MIN_BLOCKS) k_shade_vert
 // per issue, profiles/r02_nee_sort_*); a launch that compiles only one branch halves the footprint.
 // Samples are the same samples; only the order of the shadow records (and of the energy atomics behind them) changes.
 enum : int { NEE_BOTH = 0, NEE_LIGHT = 1, NEE_ENV = 2 };
+enum : int { NEE_MODE_BOTH = 0, NEE_MODE_LIGHT_ONLY = 1, NEE_MODE_SORTED = 2 };
 #define NEE_RING 64u
 struct NeeVertex {
   float3 p, nrm, wi;
@@ -1189,12 +1190,12 @@ struct NeeVertex {
   Frame frame;
   GgxParams gp;
 };
-template <uint32_t CLASS, int KIND>
+template <uint32_t CLASS, int KIND, bool SORTED>
 __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx R, uint32_t bounce, const NeeRec *__restrict__ nee,
                                                          uint32_t *__restrict__ counts, float4 *__restrict__ sh_a, float4 *__restrict__ sh_b,
                                                          uint32_t *__restrict__ sh_c) {
   __shared__ WarpChunk s_chunks[SHADE_THREADS / 32][NEE_BINS];
-  constexpr bool SORTED = KIND != NEE_BOTH;
+  static_assert(!(SORTED && KIND == NEE_BOTH), "a sorted launch draws one kind");
   __shared__ uint2 s_ring[SORTED ? SHADE_THREADS / 32 : 1][SORTED ? NEE_RING : 1];  // (record, sample index) per parked item
   WarpChunk *st_shadow = s_chunks[threadIdx.x >> 5];
   const uint32_t n = counts[CLASS == Q_DIFFUSE ? Q_NEE_DIFFUSE : Q_NEE_GGX];
@@ -1253,7 +1254,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
       RptRand4 sn = rpt_philox(R.seed, v.pixel, v.sample, rpt_block_nee(bounce, L, ls));
       float pick;
       bool sample_world = choose(sn.x, S.p_env, pick);  // pt.rs:350-353
-      if (KIND == NEE_LIGHT) sample_world = false;  // (what the classification found; lets the compiler drop the other branch)
+      // one kind per launch: what the classification found (SORTED), or the only kind the scene has (p_env = 0, where
+      // choose() cannot return anything else); lets the compiler drop the other branch
+      if (KIND == NEE_LIGHT) sample_world = false;
       if (KIND == NEE_ENV) sample_world = true;
       float3 dir = f3(0, 0, 1);
       float light_pdf = 0.0f, emission = 1.0f;
@@ -1923,6 +1926,16 @@ __global__ void __launch_bounds__(256) k_probe_bw(const float4 *__restrict__ src
   if (acc == 123.456f) *sink = acc;  // keeps the loads alive
 }
 
+__global__ void k_debug_env_roundtrip(uint32_t n, const float *__restrict__ u, const float *__restrict__ v, int which, float *__restrict__ uo,
+                                      float *__restrict__ vo) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 ident[3] = {make_float4(1, 0, 0, 0), make_float4(0, 1, 0, 0), make_float4(0, 0, 1, 0)};
+  const float2 q = which ? uv_roundtrip_unrotated_cr(u[i], v[i]) : direction_to_uv_cr(xform_vec(ident, uv_to_direction_cr(u[i], v[i])));
+  uo[i] = q.x;
+  vo[i] = q.y;
+}
+
 // generic closest-hit query of host-provided rays (rpt_trace_rays)
 template <int MODE>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32_t n, const float *__restrict__ o, const float *__restrict__ d,
@@ -2059,7 +2072,7 @@ struct RptScene {
   uint32_t env_stack_count = 0;  // textures in the environment's stack (HDR)
   bool has_ggx = true;     // any material of the GGX class (else its shade kernel is never launched)
   bool fused_shade = false;  // RPT_FUSED_SHADE=1: the round-1 single shade kernel instead of k_shade_vertex + k_nee
-  bool mixed_nee = false;  // k_nee<., NEE_LIGHT> + k_nee<., NEE_ENV>: samples sorted by kind before they are drawn
+  int nee_mode = 0;  // NEE_MODE_*: which form of k_nee the scene's NEE sample generation takes
   int trav_mode = TRAV_BVH;  // TRAV_SMALL (RPT_SMALL=1) for scenes of <= RPT_SMALL_MAX leaves without a BLAS;
                              // TRAV_BVH_TMA: k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
   size_t counts_cap = 0;     // bounces the per-bounce counter block has room for
@@ -2362,6 +2375,22 @@ void launch_shadow(RptScene *S, const WaveBuffers &w, cudaStream_t st, bool stat
 #undef RPT_SHADOW_LAUNCH
 }
 
+// NEE sample generation over one class's hand-over queue, in the form the scene was given at rpt_scene_create (nee_mode).
+template <uint32_t CLASS>
+void launch_nee(RptScene *S, int slot, cudaStream_t st, const RenderCtx &R, uint32_t b, const NeeRec *q, uint32_t *cb, const WaveBuffers &w) {
+#define RPT_NEE_LAUNCH(KIND, SORTED) k_nee<CLASS, KIND, SORTED><<<S->grid[slot], SHADE_THREADS, 0, st>>>(S->dev, R, b, q, cb, w.sh_a, w.sh_b, w.sh_c)
+  switch (S->nee_mode) {
+    case NEE_MODE_SORTED:
+      RPT_NEE_LAUNCH(NEE_LIGHT, true);
+      RPT_NEE_LAUNCH(NEE_ENV, true);
+      S->kernel_launches[slot] += 1;  // (one timing span, two launches)
+      break;
+    case NEE_MODE_LIGHT_ONLY: RPT_NEE_LAUNCH(NEE_LIGHT, false); break;
+    default: RPT_NEE_LAUNCH(NEE_BOTH, false); break;
+  }
+#undef RPT_NEE_LAUNCH
+}
+
 // Renders P->spp samples per pixel into S->film (un-normalised sum). Fills counters.
 int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   if (int rc = validate(S, P)) return rc;
@@ -2566,23 +2595,11 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
           }
           if (P->light_samples > 0) {
             T.begin(K_NEE_DIFFUSE);
-            if (S->mixed_nee) {
-              k_nee<Q_DIFFUSE, NEE_LIGHT><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
-              k_nee<Q_DIFFUSE, NEE_ENV><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
-              S->kernel_launches[K_NEE_DIFFUSE] += 1;  // (one timing span, two launches)
-            } else {
-              k_nee<Q_DIFFUSE, NEE_BOTH><<<S->grid[K_NEE_DIFFUSE], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_d, cb, w.sh_a, w.sh_b, w.sh_c);
-            }
+            launch_nee<Q_DIFFUSE>(S, K_NEE_DIFFUSE, st, R, b, w.nee_d, cb, w);
             T.end();
             if (S->has_ggx) {
               T.begin(K_NEE_GGX);
-              if (S->mixed_nee) {
-                k_nee<Q_GGX, NEE_LIGHT><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
-                k_nee<Q_GGX, NEE_ENV><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
-                S->kernel_launches[K_NEE_GGX] += 1;
-              } else {
-                k_nee<Q_GGX, NEE_BOTH><<<S->grid[K_NEE_GGX], SHADE_THREADS, 0, st>>>(S->dev, R, b, w.nee_g, cb, w.sh_a, w.sh_b, w.sh_c);
-              }
+              launch_nee<Q_GGX>(S, K_NEE_GGX, st, R, b, w.nee_g, cb, w);
               T.end();
             }
           }
@@ -3098,6 +3115,16 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   if (E.kind == RPT_ENV_HDR && E.texstack >= 0 && (uint32_t)E.texstack < d->num_texstacks) S->env_stack_count = d->texstacks[E.texstack].count;
   to3x4(E.rot_forward, D.env_rot_fwd);
   to3x4(E.rot_reverse, D.env_rot_rev);
+  {
+    // An unrotated environment (every shipped scene but one) takes the libm-free uv round trip; RPT_ENV_FAST=0 keeps the libm path.
+    bool ident = true;
+    for (int r = 0; r < 3; ++r) {
+      const float *f = &D.env_rot_fwd[r].x, *v = &D.env_rot_rev[r].x;
+      for (int c = 0; c < 3; ++c) ident = ident && f[c] == (r == c ? 1.0f : 0.0f) && v[c] == (r == c ? 1.0f : 0.0f);
+    }
+    const char *e = std::getenv("RPT_ENV_FAST");
+    D.env_unrotated = ident && !(e && e[0] == '0');
+  }
   if (E.kind == RPT_ENV_HDR && E.imap_rows) {
     size_t n = (size_t)E.imap_rows * E.imap_cols;
     D.imap_rows = E.imap_rows;
@@ -3198,16 +3225,29 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     S->grid[K_SHADE_DIFFUSE] = occupancy_grid(k_shade_vertex<Q_DIFFUSE>, SHADE_THREADS, 0, S->num_sms);
     S->grid[K_SHADE_GGX] = occupancy_grid(k_shade_vertex<Q_GGX>, SHADE_THREADS, 0, S->num_sms);
     {
-      // parked (vertex, sample) items sorted by kind: only where both kinds occur (see k_nee); RPT_NEE_SORT=0 / 1 overrides
+      // Which form of k_nee the scene gets: light samples only (p_env = 0: the environment branch is not even compiled in),
+      // both kinds sorted (0 < p_env < 1: one launch per kind over parked (vertex, sample) pairs; see k_nee), or the plain
+      // two-kind loop (p_env = 1: the environment-only instantiation spills more than the loop that carries both branches).
+      // RPT_NEE_SORT=0 selects the plain loop, RPT_NEE_SORT=1 the sorted form, whatever p_env is.
       const char *e = std::getenv("RPT_NEE_SORT");
-      S->mixed_nee = e ? e[0] == '1' : (S->dev.p_env > 0.0f && S->dev.p_env < 1.0f);
+      const float pe = S->dev.p_env;
+      if (e && e[0] == '1') S->nee_mode = NEE_MODE_SORTED;
+      else if (e && e[0] == '0') S->nee_mode = NEE_MODE_BOTH;
+      else S->nee_mode = pe <= 0.0f ? NEE_MODE_LIGHT_ONLY : (pe >= 1.0f ? NEE_MODE_BOTH : NEE_MODE_SORTED);
     }
-    if (S->mixed_nee) {  // (the two kinds share a grid size: the smaller of their occupancies)
-      S->grid[K_NEE_DIFFUSE] = std::min(occupancy_grid(k_nee<Q_DIFFUSE, NEE_LIGHT>, SHADE_THREADS, 0, S->num_sms), occupancy_grid(k_nee<Q_DIFFUSE, NEE_ENV>, SHADE_THREADS, 0, S->num_sms));
-      S->grid[K_NEE_GGX] = std::min(occupancy_grid(k_nee<Q_GGX, NEE_LIGHT>, SHADE_THREADS, 0, S->num_sms), occupancy_grid(k_nee<Q_GGX, NEE_ENV>, SHADE_THREADS, 0, S->num_sms));
-    } else {
-      S->grid[K_NEE_DIFFUSE] = occupancy_grid(k_nee<Q_DIFFUSE, NEE_BOTH>, SHADE_THREADS, 0, S->num_sms);
-      S->grid[K_NEE_GGX] = occupancy_grid(k_nee<Q_GGX, NEE_BOTH>, SHADE_THREADS, 0, S->num_sms);
+    switch (S->nee_mode) {
+      case NEE_MODE_SORTED:  // (the two kinds share a grid size: the smaller of their occupancies)
+        S->grid[K_NEE_DIFFUSE] = std::min(occupancy_grid(k_nee<Q_DIFFUSE, NEE_LIGHT, true>, SHADE_THREADS, 0, S->num_sms), occupancy_grid(k_nee<Q_DIFFUSE, NEE_ENV, true>, SHADE_THREADS, 0, S->num_sms));
+        S->grid[K_NEE_GGX] = std::min(occupancy_grid(k_nee<Q_GGX, NEE_LIGHT, true>, SHADE_THREADS, 0, S->num_sms), occupancy_grid(k_nee<Q_GGX, NEE_ENV, true>, SHADE_THREADS, 0, S->num_sms));
+        break;
+      case NEE_MODE_LIGHT_ONLY:
+        S->grid[K_NEE_DIFFUSE] = occupancy_grid(k_nee<Q_DIFFUSE, NEE_LIGHT, false>, SHADE_THREADS, 0, S->num_sms);
+        S->grid[K_NEE_GGX] = occupancy_grid(k_nee<Q_GGX, NEE_LIGHT, false>, SHADE_THREADS, 0, S->num_sms);
+        break;
+      default:
+        S->grid[K_NEE_DIFFUSE] = occupancy_grid(k_nee<Q_DIFFUSE, NEE_BOTH, false>, SHADE_THREADS, 0, S->num_sms);
+        S->grid[K_NEE_GGX] = occupancy_grid(k_nee<Q_GGX, NEE_BOTH, false>, SHADE_THREADS, 0, S->num_sms);
+        break;
     }
   }
   S->grid[K_FILM] = occupancy_grid(k_film, 256, film_smem, S->num_sms);
@@ -3479,6 +3519,23 @@ int rpt_probe_bandwidth(int device, uint64_t bytes, uint32_t reps, int mode, dou
   cudaFree(sink);
   CUDA_TRY(cudaGetLastError());
   *gbps = best;
+  return 0;
+}
+
+// Test hook (not in rpt.h): the uv -> direction -> uv round trip of an unrotated HDR environment through the libm path
+// (which = 0) or the libm-free path (which = 1), n pairs, on `device`.
+int rpt_debug_env_roundtrip(int device, uint32_t n, const float *u, const float *v, int which, float *u_out, float *v_out) {
+  if (!u || !v || !u_out || !v_out) return fail("null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  float *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 4 * (size_t)n * sizeof(float)));
+  CUDA_TRY(cudaMemcpy(d, u, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d + n, v, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  k_debug_env_roundtrip<<<(n + 255) / 256, 256>>>(n, d, d + n, which, d + 2 * (size_t)n, d + 3 * (size_t)n);
+  CUDA_TRY(cudaMemcpy(u_out, d + 2 * (size_t)n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(v_out, d + 3 * (size_t)n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

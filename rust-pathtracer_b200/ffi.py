@@ -372,6 +372,21 @@ def probe_bandwidth(lib: ct.CDLL, device: int, nbytes: int, reps: int, mode: int
     return float(out.value)
 
 
+def debug_env_roundtrip(lib: ct.CDLL, device: int, u: np.ndarray, v: np.ndarray, fast: bool):
+    """rpt_debug_env_roundtrip (a test hook of the product library, not part of rpt.h): the uv -> direction -> uv round trip of an
+    unrotated HDR environment on the device, through libm (fast=False) or the libm-free path (fast=True)."""
+    u = np.ascontiguousarray(u, np.float32)
+    v = np.ascontiguousarray(v, np.float32)
+    uo, vo = np.empty_like(u), np.empty_like(v)
+    fp = ct.POINTER(ct.c_float)
+    fn = lib.rpt_debug_env_roundtrip
+    fn.argtypes = [ct.c_int, c_u32, fp, fp, ct.c_int, fp, fp]
+    fn.restype = ct.c_int
+    if fn(device, len(u), u.ctypes.data_as(fp), v.ctypes.data_as(fp), int(fast), uo.ctypes.data_as(fp), vo.ctypes.data_as(fp)) != 0:
+        raise RptError(lib.rpt_last_error().decode("utf-8", "replace"))
+    return uo, vo
+
+
 class Scene:
     """RAII wrapper over an RptScene* of either library (product or oracle)."""
 

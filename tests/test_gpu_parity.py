@@ -589,6 +589,62 @@ def test_nee_samples_sorted_by_kind_equal_unsorted(monkeypatch, name):
     srt.close()
 
 
+def env_roundtrip_inputs(rng, n):
+    """(u, v) pairs for the uv -> direction -> uv round trip: uniform, importance-map grid points (1000 and 4096 x 2048), near
+    and at both poles, both sides of the azimuth seam. 9 regimes of n pairs."""
+    f32 = np.float32
+    parts = [
+        (rng.random(n, dtype=f32), rng.random(n, dtype=f32)),
+        ((rng.integers(0, 1001, n) / 1000).astype(f32), (rng.integers(0, 1001, n) / 1000).astype(f32)),
+        ((rng.integers(0, 4097, n) / 4096).astype(f32), (rng.integers(0, 2049, n) / 2048).astype(f32)),
+        (rng.random(n, dtype=f32), (rng.random(n, dtype=f32) * f32(2e-3)).astype(f32)),
+        (rng.random(n, dtype=f32), (rng.random(n, dtype=f32) * f32(2e-5)).astype(f32)),
+        (rng.random(n, dtype=f32), (f32(1) - rng.random(n, dtype=f32) * f32(1e-3)).astype(f32)),
+        ((rng.random(n, dtype=f32) * f32(1e-4)).astype(f32), rng.random(n, dtype=f32)),
+        ((f32(1) - rng.random(n, dtype=f32) * f32(1e-4)).astype(f32), rng.random(n, dtype=f32)),
+        (rng.random(n, dtype=f32), rng.integers(0, 2, n).astype(f32)),  # the poles themselves (x = y = +-0: atan2 goes by the signs)
+    ]
+    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+
+def test_env_roundtrip_fast_path():
+    """uv_roundtrip_unrotated_cr (the HDR environment's uv -> direction -> uv round trip without f64 atan2 / acos, used when the
+    environment is unrotated) returns the f32 values of the libm path it replaces: 18 M inputs over every regime; the two device
+    paths may differ only where the two f64 evaluations straddle an f32 rounding boundary (both are ~1 ulp of f64 from the exact
+    value), which is allowed for at most 1 input in a million and by at most one f32 ulp."""
+    p = parity.pkg()
+    lib = p.ffi.load_library()
+    u, v = env_roundtrip_inputs(np.random.default_rng(3), 2_000_000)
+    u0, v0 = p.ffi.debug_env_roundtrip(lib, 0, u, v, fast=False)
+    u1, v1 = p.ffi.debug_env_roundtrip(lib, 0, u, v, fast=True)
+    assert np.isfinite(u1).all() and np.isfinite(v1).all()
+    for a, b, what in ((u0, u1, "u"), (v0, v1, "v")):
+        diff = a != b
+        assert diff.mean() <= 1e-6, (what, int(diff.sum()))
+        if diff.any():
+            ulp = np.abs(a[diff].view(np.int32).astype(np.int64) - b[diff].view(np.int32).astype(np.int64))
+            assert ulp.max() <= 1, (what, int(ulp.max()))
+
+
+@pytest.mark.parametrize("name", ["hdri2", "hdri"])
+def test_env_fast_roundtrip_renders_the_same_film(monkeypatch, name):
+    """RPT_ENV_FAST=0 keeps the libm round trip: same counters, same film (identical texels are read)."""
+    world, st, flat = parity.load_scene(name, 192, 108, 8)
+    monkeypatch.setenv("RPT_ENV_FAST", "0")
+    slow = parity.cuda_scene(flat)
+    monkeypatch.delenv("RPT_ENV_FAST")
+    fast = parity.cuda_scene(flat)
+    p = st.params(seed=37)
+    f0, c0 = slow.render_pt(p)
+    f1, c1 = fast.render_pt(p)
+    for k in ("segments", "bounce_rays", "shadow_rays", "shadow_rays_traced", "env_hits", "nee_vertices"):
+        assert getattr(c0, k) == getattr(c1, k), (name, k)
+    ok = np.isfinite(f0)
+    assert np.array_equal(ok, np.isfinite(f1)) and np.allclose(f0[ok], f1[ok], rtol=1e-5, atol=1e-9)
+    slow.close()
+    fast.close()
+
+
 @pytest.mark.parametrize("name", ["cornell", "kitchen_sink", "hdri2"])
 def test_two_stream_half_waves_equal_single_stream(monkeypatch, name):
     """RPT_OVERLAP=1 (a wave cut into two half-waves on two streams; opt-in after measurement, profiles/r02_overlap.md) renders

@@ -334,6 +334,52 @@ def test_bvh4_collapse_encloses_what_the_binary_tree_does(tmp_path):
     assert out.stdout.count("fails=0") == 18, out.stdout
 
 
+def test_env_roundtrip_identity_against_libm():
+    """The identity behind uv_roundtrip_unrotated_cr (csrc/rpt_device.cuh): for the f32 direction d that uv_to_direction_cr makes of
+    the angles (a, b), atan2(d.y, d.x) = a + atan2(d.y cos a - d.x sin a, d.x cos a + d.y sin a) and acos(d.z) = b +
+    atan2(w cos b - d.z sin b, d.z cos b + w sin b), w = sqrt((1 - d.z)(1 + d.z)), each evaluated in f64 with the small-angle
+    series and rounded to f32 once. Restated in numpy (f64, the same guards and fall-backs) and compared with numpy's libm atan2 /
+    acos over every regime (uniform, importance-map grid points, both poles, the azimuth seam): the f32 results are identical."""
+    f32, f64 = np.float32, np.float64
+    TAU, PI = f32(6.28318530717958647692), f32(3.14159265358979323846)
+
+    def both(u, v):
+        a, b = ((u - f32(0.5)) * TAU).astype(f32), (v * PI).astype(f32)
+        ad, bd = a.astype(f64), b.astype(f64)
+        st, ct, sp, cp = np.sin(ad), np.cos(ad), np.sin(bd), np.cos(bd)
+        fsp = sp.astype(f32)
+        x = (fsp * ct.astype(f32)).astype(f32).astype(f64)
+        y = (fsp * st.astype(f32)).astype(f32).astype(f64)
+        z = cp.astype(f32).astype(f64)
+        th_libm, ph_libm = np.arctan2(y, x).astype(f32), np.arccos(z).astype(f32)
+        c, s = x * ct + y * st, y * ct - x * st
+        t = s / np.where(c > 1e-30, c, 1.0)
+        th = ad + t * (1.0 - t * t / 3.0)
+        th = np.where(th > np.pi, th - 2 * np.pi, np.where(th < -np.pi, th + 2 * np.pi, th))
+        th = np.where((c > 1e-30) & (np.abs(t) < 1e-3), th.astype(f32), th_libm)
+        w = np.sqrt((1.0 - z) * (1.0 + z))
+        c2, s2 = z * cp + w * sp, w * cp - z * sp
+        t2 = s2 * (2.0 - c2)
+        ph = np.where((np.abs(z) != 1.0) & (np.abs(t2) < 1e-3), (bd + t2 * (1.0 - t2 * t2 / 3.0)).astype(f32), ph_libm)
+        return th_libm, ph_libm, th, ph
+
+    rng = np.random.default_rng(1)
+    n = 1_000_000
+    regimes = {
+        "uniform": (rng.random(n, dtype=f32), rng.random(n, dtype=f32)),
+        "grid 1000": ((rng.integers(0, 1001, n) / 1000).astype(f32), (rng.integers(0, 1001, n) / 1000).astype(f32)),
+        "grid 4096x2048": ((rng.integers(0, 4097, n) / 4096).astype(f32), (rng.integers(0, 2049, n) / 2048).astype(f32)),
+        "north pole": (rng.random(n, dtype=f32), (rng.random(n, dtype=f32) * f32(2e-3)).astype(f32)),
+        "south pole": (rng.random(n, dtype=f32), (f32(1) - rng.random(n, dtype=f32) * f32(1e-3)).astype(f32)),
+        "seam low": ((rng.random(n, dtype=f32) * f32(1e-4)).astype(f32), rng.random(n, dtype=f32)),
+        "seam high": ((f32(1) - rng.random(n, dtype=f32) * f32(1e-4)).astype(f32), rng.random(n, dtype=f32)),
+    }
+    for name, (u, v) in regimes.items():
+        th0, ph0, th1, ph1 = both(u, v)
+        assert np.array_equal(th0, th1), (name, int((th0 != th1).sum()))
+        assert np.array_equal(ph0, ph1), (name, int((ph0 != ph1).sum()))
+
+
 def test_exr_writer_roundtrip(pkg, tmp_path):
     """output_film's EXR payload (tonemap/mod.rs:225-247): the writer's file is read back by the package's own reader and,
     when OpenCV was built with OpenEXR, by an independent decoder."""
