@@ -2621,7 +2621,9 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
     T.begin(K_FILM);
     k_film<<<S->grid[K_FILM], 256, film_smem, S->stream>>>(S->dev, Rw, S->wave.acc, S->film);
     T.end();
-    CUDA_TRY(cudaMemcpyAsync(h_counts.data(), S->wave.counts, h_counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, S->stream));
+    for (int k = 0; k < parts; ++k)  // (only the rows this job zeroed and used: the rest of the block is never written)
+      CUDA_TRY(cudaMemcpyAsync(h_counts.data() + (size_t)k * rows * Q_COUNT, S->wave.counts + (size_t)k * rows * Q_COUNT, n_counts * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, S->stream));
     CUDA_TRY(cudaStreamSynchronize(S->stream));
     CUDA_TRY(cudaGetLastError());
     // Profile counters (profile.rs:1-8) from the queue sizes
