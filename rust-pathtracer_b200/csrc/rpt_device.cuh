@@ -608,7 +608,10 @@ __device__ __forceinline__ bool tri_test_pre(float3 p0, float3 p1, float3 p2, fl
 // only on the sign of the ray direction, so the six plane rows are fetched through three per-ray row offsets and the slab test
 // needs no min / max per box; the (up to four) children that are hit are visited nearest first. Boxes, leaves and the
 // accept() rule are those of the two-wide tree, so the result is the same hit (tests/test_gpu_parity.py::test_bvh4_*).
-template <bool WIDE>
+// TWO_LEVEL = false is the walk for scenes whose TLAS leaves are all triangles and analytic shapes (no transformed mesh
+// instance: Cornell, the furnace, the HDR scenes): the instance-local ray, the BLAS bookkeeping and the change-of-space code
+// are compiled out, which frees ~10 registers of state.
+template <bool WIDE, bool TWO_LEVEL = true>
 struct TravT {
   float3 o, d;       // world-space ray
   float3 ro, rd;     // current-space ray (instance-local inside a BLAS)
@@ -622,11 +625,21 @@ struct TravT {
   bool found;
   TraceHit out;
 
+  // The watertight-test constants (three IEEE divisions) are computed eagerly only for the world-space ray at init(), where the
+  // whole warp does it together. After a change of space (entering or leaving a mesh instance: 1.5 of each per ray on the
+  // instanced 10 M-triangle scene, taken by 2.5-4.3 lanes at a time) they are only marked stale (kz = 3) and rebuilt by the
+  // first triangle test that needs them - many instance visits end in the BLAS's boxes without reaching a triangle.
+  template <bool EAGER>
   __device__ __forceinline__ void set_space(float3 no, float3 nd) {
     ro = no;
     rd = nd;
     slab_recip(ro, rd, inv, oinv);
+#ifdef RPT_EAGER_TRI_SETUP  // (A/B build: the constants rebuilt at every change of space)
     tr = tri_ray_setup(rd);
+#else
+    if (EAGER) tr = tri_ray_setup(rd);
+    else tr.kz = 3u;
+#endif
     if (WIDE) near_rows = (inv.x < 0.0f ? 3u : 0u) | (inv.y < 0.0f ? 4u : 1u) << 8 | (inv.z < 0.0f ? 5u : 2u) << 16;
   }
   __device__ __forceinline__ void init(const DevScene &S, float3 o_, float3 d_, float tmax_) {
@@ -643,12 +656,12 @@ struct TravT {
     cur = WIDE ? S.tlas_root4 : S.tlas_root;
     cur_inst = RPT_NONE;
     cur_inst_order = cur_tri_base = 0;
-    set_space(o, d);
+    set_space<true>(o, d);
   }
   // Pops the next node ref; leaving a BLAS (its stack segment is exhausted) restores the world-space ray.
   __device__ __forceinline__ int pop(const int *stack, int stride) {
-    if (cur_inst != RPT_NONE && sp == blas_base) {
-      set_space(o, d);
+    if (TWO_LEVEL && cur_inst != RPT_NONE && sp == blas_base) {
+      set_space<false>(o, d);
       cur_inst = RPT_NONE;
     }
     if (sp == 0) return RPT_DONE;
@@ -758,7 +771,7 @@ struct TravT {
       uint32_t tri = 0, tri_local = idx, hit_inst = cur_inst, inst_order = cur_inst_order;
       int next = 0;
       bool have_next = false;
-      if (cur_inst != RPT_NONE) {
+      if (TWO_LEVEL && cur_inst != RPT_NONE) {
         tri = cur_tri_base + idx;  // BLAS leaf: a triangle of the current mesh instance
       } else {
         uint4 lf = __ldg(S.tlas_leaves + idx);
@@ -779,9 +792,9 @@ struct TravT {
             ld = xform_vec(I.rev, d);
           }
           uint32_t kind = flags & DI_KIND_MASK;
-          if (kind == RPT_AGG_MESH) {
+          if (TWO_LEVEL && kind == RPT_AGG_MESH) {  // (a scene that gets the one-level walk has no such leaf)
             blas_base = sp;
-            set_space(lo, ld);
+            set_space<false>(lo, ld);
             cur_inst = hit_inst;
             cur_inst_order = inst_order;
             cur_tri_base = I.tri_base;
@@ -807,6 +820,9 @@ struct TravT {
         const float4 *tv = S.tri_verts + 3 * (size_t)tri;
         float4 v0 = __ldg(tv), v1 = __ldg(tv + 1), v2 = __ldg(tv + 2);
         float t, b0, b1, b2;
+#ifndef RPT_EAGER_TRI_SETUP
+        if (tr.kz > 2u) tr = tri_ray_setup(rd);
+#endif
         if (tri_test_pre(f3(v0), f3(v1), f3(v2), ro, tr, 0.0f, closest, t, b0, b1, b2) &&
             accept(t, tie_key(false, inst_order, __float_as_uint(v1.w)), hit_inst, tri_local) && ANY_HIT)
           return true;
@@ -819,10 +835,10 @@ struct TravT {
 
 using Trav = TravT<false>;
 
-template <bool ANY_HIT, bool STATS, bool WIDE = false>
+template <bool ANY_HIT, bool STATS, bool WIDE = false, bool TWO_LEVEL = true>
 __device__ __forceinline__ bool trace_ray(const DevScene &S, float3 o, float3 d, float tmax, int *stack, int stride, TraceHit &out,
                                           TraceWork &work) {
-  TravT<WIDE> t;
+  TravT<WIDE, TWO_LEVEL> t;
   t.init(S, o, d, tmax);
   t.template run<ANY_HIT, STATS>(S, stack, stride, work);
   out = t.out;

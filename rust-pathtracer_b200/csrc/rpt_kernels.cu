@@ -316,6 +316,9 @@ struct TileStream {
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 8  // resident CTAs per SM the traversal kernels are compiled for (register cap = 65536 / (128 * this))
 #endif
+#ifndef TRACE_MIN_BLOCKS_FLAT
+#define TRACE_MIN_BLOCKS_FLAT TRACE_MIN_BLOCKS  // the one-level walk (TRAV_BVH_FLAT) needs no spills at 64 registers; tighter caps: profiles/r02_flat_walk.txt
+#endif
 #ifndef TRACE_MIN_BLOCKS_WIDE
 #define TRACE_MIN_BLOCKS_WIDE 6  // the four-wide walk holds seven 128-bit node rows in flight: 80 registers instead of 64
 #endif
@@ -394,8 +397,10 @@ __device__ __forceinline__ uint32_t material_class(const DevScene &S, uint32_t m
 // Closest-hit traversal of the path queue; appends each path to the list of its vertex's class.
 // RAYGEN: the launch of bounce 0 generates its camera vertices itself (and writes them out for the shade kernel) instead
 // of reading what a separate ray-generation kernel wrote: one 64-byte queue write + read per sample less.
-enum : int { TRAV_BVH = 0, TRAV_BVH_TMA = 1, TRAV_SMALL = 2, TRAV_BVH_REFILL = 3, TRAV_BVH4 = 4 };  // how the traversal kernels find hits (chosen per scene)
+enum : int { TRAV_BVH = 0, TRAV_BVH_TMA = 1, TRAV_SMALL = 2, TRAV_BVH_REFILL = 3, TRAV_BVH4 = 4, TRAV_BVH_FLAT = 5 };  // how the traversal kernels find hits (chosen per scene)
 
+// TRAV_BVH_FLAT: TRAV_BVH for scenes without a transformed mesh instance (TravT<., TWO_LEVEL = false>); chosen automatically,
+// RPT_FLAT=0 keeps the two-level walk.
 // TRAV_BVH4 (RPT_BVH4=1): the same trees collapsed to four children per node (rpt::collapse_bvh4, TravT<true>): half the
 // dependent node fetches per ray, one 128-byte line per node, no per-box min / max.
 
@@ -416,7 +421,7 @@ __device__ __forceinline__ void stage_small_tris(const DevScene &S, float4 *s_tr
 }
 
 template <int MODE, bool RAYGEN, bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WIDE : TRACE_MIN_BLOCKS) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
+__global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WIDE : (MODE == 5 ? TRACE_MIN_BLOCKS_FLAT : TRACE_MIN_BLOCKS)) k_trace(DevScene S, const PathRec *__restrict__ paths, HitRec *__restrict__ hits,
                                                          uint32_t *__restrict__ q_miss, uint32_t *__restrict__ q_diffuse,
                                                          uint32_t *__restrict__ q_ggx, uint32_t *__restrict__ counts,
                                                          unsigned long long *__restrict__ work, float *__restrict__ acc,
@@ -506,7 +511,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WI
       hit = sv.found;
       th = sv.out;
     } else if (active) {
-      hit = trace_ray<false, STATS, MODE == TRAV_BVH4>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+      hit = trace_ray<false, STATS, MODE == TRAV_BVH4, MODE != TRAV_BVH_FLAT>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
     }
     if (active) {
       HitRec h;
@@ -1453,12 +1458,13 @@ __device__ __forceinline__ void shadow_light_contribution(const DevScene &S, flo
 // NEE visibility. Light samples: closest hit, accepted when ANY light-material surface is hit, whose own
 // emission is used (pt.rs:177-218, F9). Environment samples: any hit kills the sample (pt.rs:254-263).
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WIDE : TRACE_MIN_BLOCKS) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
+__global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WIDE : (MODE == 5 ? TRACE_MIN_BLOCKS_FLAT : TRACE_MIN_BLOCKS)) k_shadow(DevScene S, const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b,
                                                           const uint32_t *__restrict__ sh_c, uint32_t *__restrict__ counts,
                                                           float *__restrict__ acc, unsigned long long *__restrict__ work) {
   extern __shared__ int s_stack[];
   constexpr bool SMALL = MODE == TRAV_SMALL;
   constexpr bool WIDE = MODE == TRAV_BVH4;
+  constexpr bool TWO_LEVEL = MODE != TRAV_BVH_FLAT;
   const float4 *s_tris = reinterpret_cast<const float4 *>(s_stack);
   if (SMALL) stage_small_tris(S, reinterpret_cast<float4 *>(s_stack));
   TraceWork tw{0, 0, 0};
@@ -1523,7 +1529,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WI
       return;
     }
     if (env_ray) {
-      if (!trace_ray<true, STATS, WIDE>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) atomicAdd(acc + slot, pre);
+      if (!trace_ray<true, STATS, WIDE, TWO_LEVEL>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw)) atomicAdd(acc + slot, pre);
       return;
     }
     bool lit;
@@ -1534,7 +1540,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WI
       uint64_t key_l = 0;
       uint32_t inst_l = RPT_NONE;
       if (!shadow_closest_light<STATS>(S, o, d, tl, key_l, inst_l, tw)) return;  // no light along the ray: nothing to add
-      TravT<WIDE> tv;
+      TravT<WIDE, TWO_LEVEL> tv;
       tv.init(S, o, d, RPT_INF);
       tv.closest = tl;  // only geometry that beats the light (closer, or equal t with a winning tie key) is accepted
       tv.best_key = key_l;
@@ -1545,7 +1551,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE == 4 ? TRACE_MIN_BLOCKS_WI
       th.inst = inst_l;
       th.prim = 0;
     } else {
-      lit = trace_ray<false, STATS, WIDE>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+      lit = trace_ray<false, STATS, WIDE, TWO_LEVEL>(S, o, d, RPT_INF, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
     }
     if (lit) shadow_light_contribution(S, o, d, th, pre, lambda, slot, acc);
   };
@@ -1961,7 +1967,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DevScene S, uint32
       sv.template run<false, false>(S, reinterpret_cast<const float4 *>(s_stack), ro, rd, tm, active, tw);
       th = sv.out;
     } else if (active) {
-      trace_ray<false, false, MODE == TRAV_BVH4>(S, ro, rd, tm, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
+      trace_ray<false, false, MODE == TRAV_BVH4, MODE != TRAV_BVH_FLAT>(S, ro, rd, tm, s_stack + threadIdx.x, TRACE_THREADS, th, tw);
     }
     if (active) {
       HitRec h;
@@ -2072,6 +2078,7 @@ struct RptScene {
   uint32_t env_stack_count = 0;  // textures in the environment's stack (HDR)
   bool has_ggx = true;     // any material of the GGX class (else its shade kernel is never launched)
   bool fused_shade = false;  // RPT_FUSED_SHADE=1: the round-1 single shade kernel instead of k_shade_vertex + k_nee
+  bool flat_tlas = false;  // no transformed mesh instance: every TLAS leaf is a triangle or an analytic shape
   int nee_mode = 0;  // NEE_MODE_*: which form of k_nee the scene's NEE sample generation takes
   int trav_mode = TRAV_BVH;  // TRAV_SMALL (RPT_SMALL=1) for scenes of <= RPT_SMALL_MAX leaves without a BLAS;
                              // TRAV_BVH_TMA: k_trace reads its queue through TMA-staged shared-memory tiles (RPT_TMA_TILES=1)
@@ -2346,6 +2353,8 @@ void launch_trace(RptScene *S, const WaveBuffers &w, cudaStream_t st, bool stats
     if (stats) RPT_TRACE_LAUNCH(TRAV_SMALL, true); else RPT_TRACE_LAUNCH(TRAV_SMALL, false);
   } else if (S->trav_mode == TRAV_BVH_REFILL) {
     if (stats) RPT_TRACE_LAUNCH(TRAV_BVH_REFILL, true); else RPT_TRACE_LAUNCH(TRAV_BVH_REFILL, false);
+  } else if (S->trav_mode == TRAV_BVH_FLAT) {
+    if (stats) RPT_TRACE_LAUNCH(TRAV_BVH_FLAT, true); else RPT_TRACE_LAUNCH(TRAV_BVH_FLAT, false);
   } else if (S->trav_mode == TRAV_BVH4) {
     if (stats) RPT_TRACE_LAUNCH(TRAV_BVH4, true); else RPT_TRACE_LAUNCH(TRAV_BVH4, false);
   } else {
@@ -2367,6 +2376,8 @@ void launch_shadow(RptScene *S, const WaveBuffers &w, cudaStream_t st, bool stat
     if (stats) RPT_SHADOW_LAUNCH(TRAV_SMALL, true); else RPT_SHADOW_LAUNCH(TRAV_SMALL, false);
   } else if (S->trav_mode == TRAV_BVH_REFILL) {
     if (stats) RPT_SHADOW_LAUNCH(TRAV_BVH_REFILL, true); else RPT_SHADOW_LAUNCH(TRAV_BVH_REFILL, false);
+  } else if (S->trav_mode == TRAV_BVH_FLAT) {
+    if (stats) RPT_SHADOW_LAUNCH(TRAV_BVH_FLAT, true); else RPT_SHADOW_LAUNCH(TRAV_BVH_FLAT, false);
   } else if (S->trav_mode == TRAV_BVH4) {
     if (stats) RPT_SHADOW_LAUNCH(TRAV_BVH4, true); else RPT_SHADOW_LAUNCH(TRAV_BVH4, false);
   } else {
@@ -2915,6 +2926,9 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     if (d->instances[i].kind == RPT_AGG_MESH && !flattened[i]) needed_blas_depth = std::max(needed_blas_depth, minfo[d->instances[i].mesh].depth);
   // one push per inner node on the path; shared-memory stack sized to the scene (16 / 32 / 64 / 128 entries per thread)
   uint32_t need = tlas.max_depth + needed_blas_depth + 2;
+  S->flat_tlas = true;
+  for (uint32_t i = 0; i < d->num_instances; ++i)
+    if (d->instances[i].kind == RPT_AGG_MESH && !flattened[i]) S->flat_tlas = false;
   rpt::WideBvh tlas_wide;
   if (want_bvh4) {
     tlas_wide = rpt::collapse_bvh4(tlas);
@@ -3171,6 +3185,8 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     // Cornell box (short rays) it loses 38 %, on the gem scene 12 %.
     const char *r = std::getenv("RPT_REFILL");
     if (r && r[0] == '1' && S->trav_mode == TRAV_BVH) S->trav_mode = TRAV_BVH_REFILL;
+    const char *f = std::getenv("RPT_FLAT");
+    if (S->trav_mode == TRAV_BVH && S->flat_tlas && !(f && f[0] == '0')) S->trav_mode = TRAV_BVH_FLAT;
   }
   if (S->stack_smem > 48 * 1024) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -3197,6 +3213,13 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
     cudaFuncSetAttribute(k_shadow<TRAV_BVH4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     cudaFuncSetAttribute(k_shadow<TRAV_BVH4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     cudaFuncSetAttribute(k_trace_rays<TRAV_BVH4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_FLAT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_FLAT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_FLAT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace<TRAV_BVH_FLAT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_shadow<TRAV_BVH_FLAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_shadow<TRAV_BVH_FLAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_trace_rays<TRAV_BVH_FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   }
   if (S->trav_mode == TRAV_SMALL) {
     S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_SMALL, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
@@ -3204,6 +3227,9 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   } else if (S->trav_mode == TRAV_BVH_REFILL) {
     S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH_REFILL, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
     S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH_REFILL, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+  } else if (S->trav_mode == TRAV_BVH_FLAT) {
+    S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH_FLAT, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
+    S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH_FLAT, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
   } else if (S->trav_mode == TRAV_BVH4) {
     S->grid[K_TRACE] = occupancy_grid(k_trace<TRAV_BVH4, false, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
     S->grid[K_SHADOW] = occupancy_grid(k_shadow<TRAV_BVH4, false>, TRACE_THREADS, S->stack_smem, S->num_sms);
@@ -3336,6 +3362,8 @@ int rpt_trace_rays(RptScene *S, uint32_t n, const float *origins, const float *d
   CUDA_TRY(cudaMemcpyAsync(d_t, tmax, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, S->stream));
   if (S->trav_mode == TRAV_SMALL)
     k_trace_rays<TRAV_SMALL><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
+  else if (S->trav_mode == TRAV_BVH_FLAT)
+    k_trace_rays<TRAV_BVH_FLAT><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
   else if (S->trav_mode == TRAV_BVH4)
     k_trace_rays<TRAV_BVH4><<<S->grid[K_TRACE], TRACE_THREADS, S->stack_smem, S->stream>>>(S->dev, n, d_o, d_d, d_t, d_h);
   else

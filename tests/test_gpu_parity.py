@@ -645,6 +645,36 @@ def test_env_fast_roundtrip_renders_the_same_film(monkeypatch, name):
     fast.close()
 
 
+@pytest.mark.parametrize("name", ["cornell", "furnace", "hdri2", "test_nee_sphere", "rtiow2", "sun_test", "orb_caustic"])
+def test_one_level_walk_equals_two_level(monkeypatch, name):
+    """TRAV_BVH_FLAT (scenes without a transformed mesh instance get a walk with the instance-local ray and the BLAS bookkeeping
+    compiled out; RPT_FLAT=0 keeps the two-level walk) visits the same nodes in the same order: identical hit ids, BVH work
+    counters and path counters, film equal up to the order of the energy atomics."""
+    world, st, flat = parity.load_scene(name, 192, 108, 4)
+    monkeypatch.setenv("RPT_FLAT", "0")
+    two = parity.cuda_scene(flat)
+    monkeypatch.delenv("RPT_FLAT")
+    one = parity.cuda_scene(flat)
+    p = st.params(seed=41, flags=2)
+    f2, c2 = two.render_pt(p)
+    f1, c1 = one.render_pt(p)
+    for k in ("segments", "bounce_rays", "shadow_rays", "shadow_rays_traced", "env_hits", "nee_vertices", "walk_nodes", "walk_tris", "walk_insts",
+              "shadow_nodes", "shadow_tris", "shadow_insts"):
+        assert getattr(c2, k) == getattr(c1, k), (name, k, getattr(c2, k), getattr(c1, k))
+    ok = np.isfinite(f2)
+    assert np.array_equal(ok, np.isfinite(f1)) and np.allclose(f2[ok], f1[ok], rtol=1e-5, atol=1e-9)
+    a, b = two.trace_primary(p), one.trace_primary(p)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    rng = np.random.default_rng(7)
+    lo, hi = (-0.9, 0.9) if name != "cornell" else (0.01, 0.54)
+    o, d = axis_aligned_rays(rng, 9000, lo, hi)
+    tmax = np.full(len(o), np.inf, np.float32)
+    a, b = two.trace_rays(o, d, tmax), one.trace_rays(o, d, tmax)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    two.close()
+    one.close()
+
+
 @pytest.mark.parametrize("name", ["cornell", "kitchen_sink", "hdri2"])
 def test_two_stream_half_waves_equal_single_stream(monkeypatch, name):
     """RPT_OVERLAP=1 (a wave cut into two half-waves on two streams; opt-in after measurement, profiles/r02_overlap.md) renders
