@@ -2241,6 +2241,14 @@ void park_wave(RptScene *S) {
   S->wave_slots = S->wave_shadow = S->wave_acc = S->counts_cap = 0;
 }
 
+// true when the set parked in the device's cache would satisfy ensure_wave(S, slots, shadow_valid, bounces)
+bool cached_wave_fits(const RptScene *S, size_t slots, size_t shadow_valid, size_t bounces) {
+  if (S->device < 0 || S->device >= 64 || slots >= ((size_t)1 << 30)) return false;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  const WaveCache &c = g_wave_cache[S->device];
+  return c.valid && wave_path_cap(S, slots) <= c.slots && wave_shadow_cap(S, shadow_valid) <= c.shadow && slots <= c.acc && bounces <= c.counts_cap;
+}
+
 // slots = camera samples in a wave; shadow_valid = NEE rays a bounce can emit; bounces = per-bounce counter rows needed
 int ensure_wave(RptScene *S, size_t slots, size_t shadow_valid, size_t bounces) {
   size_t pcap = wave_path_cap(S, slots), scap = wave_shadow_cap(S, shadow_valid);
@@ -2432,6 +2440,10 @@ int render_waves(RptScene *S, const RptRenderParams *P, RptCounters *counters) {
   size_t want_slots = wh * (size_t)std::max<uint32_t>(P->spp, 1);
   if (want_slots < ((size_t)1 << 30) && wave_path_cap(S, want_slots) <= S->wave_slots &&
       wave_shadow_cap(S, want_slots * P->light_samples) <= S->wave_shadow && want_slots <= S->wave_acc && max_bounces <= S->counts_cap) {
+    spp_chunk = std::max<uint32_t>(P->spp, 1);
+  } else if (cached_wave_fits(S, want_slots, want_slots * P->light_samples, max_bounces)) {
+    // a scene created for this frame (a host that uploads, renders and destroys every frame) holds nothing yet, but the set the
+    // previous scene parked in the device's cache fits the whole job: ensure_wave() below takes it, no memory query needed
     spp_chunk = std::max<uint32_t>(P->spp, 1);
   } else if (S->budget_slots && S->budget_light_samples == P->light_samples && wh <= S->budget_slots) {
     // the wave budget of this scene is known from an earlier call with the same light_samples: the memory query below costs

@@ -21,7 +21,8 @@ def short(n):
     m = re.search(r"(k_[a-z_]+)(<[^>]*>)?", n)
     base, t = m.group(1), m.group(2) or ""
     if base in ("k_shade_surface", "k_shade_vertex", "k_nee"):
-        return base + ("<diffuse>" if "2" in t else "<ggx>")
+        first = re.search(r"(\d+)", t.split(",")[0])  # the material class is the first template argument (2 = diffuse, 3 = GGX)
+        return base + ("<diffuse>" if first and first.group(1) == "2" else "<ggx>")
     return base
 
 
