@@ -2202,6 +2202,7 @@ size_t shadow_queue_cap(const RptScene *S, size_t valid) {
   size_t shade_warps = ((size_t)std::max(S->grid[K_SHADE_DIFFUSE], S->grid[K_NEE_DIFFUSE]) + (size_t)std::max(S->grid[K_SHADE_GGX], S->grid[K_NEE_GGX])) * (SHADE_THREADS / 32);
   const size_t bins = std::max<size_t>(NBINS, NEE_BINS), chunk = std::min<size_t>(QCHUNK_BINNED, NEE_CHUNK);
   size_t tail = shade_warps * std::max<size_t>((size_t)NBINS * QCHUNK_BINNED, (size_t)NEE_BINS * NEE_CHUNK);
+  if (S->nee_mode == NEE_MODE_SORTED) tail *= 2;  // two k_nee launches per class append to the queue, each leaves its own chunk tails
   (void)bins;
   return valid + (valid * 31 + (chunk - 31) - 1) / (chunk - 31) + std::min<size_t>(valid, BIN_MIN_ITEMS) + tail + QCHUNK_BINNED;
 }
