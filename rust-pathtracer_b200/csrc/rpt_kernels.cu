@@ -206,14 +206,16 @@ __device__ __forceinline__ uint32_t chunk_append(uint32_t *counter, WarpChunk &w
 // kernels run 30 of 32 lanes on the coherent first bounce but 11-13 on unsorted later bounces.
 #define NBINS 8u
 #define QCHUNK_BINNED 128u
+// per = entries reserved per appending lane (warp-uniform, 32 * per <= CH): the lane owns [idx, idx + per).
 template <class Mark>
-__device__ __forceinline__ uint32_t chunk_append_binned(uint32_t *counter, WarpChunk *st, bool pred, uint32_t bin, Mark mark, uint32_t CH = QCHUNK_BINNED) {
+__device__ __forceinline__ uint32_t chunk_append_binned(uint32_t *counter, WarpChunk *st, bool pred, uint32_t bin, Mark mark, uint32_t CH = QCHUNK_BINNED,
+                                                        uint32_t per = 1u) {
   uint32_t active = __ballot_sync(0xFFFFFFFFu, pred);
   uint32_t idx = RPT_NONE;
   if (pred) {
     uint32_t lane = threadIdx.x & 31u;
     uint32_t group = __match_any_sync(active, bin);  // the lanes that append to the same bin
-    uint32_t leader = __ffs(group) - 1, cnt = __popc(group);
+    uint32_t leader = __ffs(group) - 1, cnt = __popc(group) * per;
     uint32_t first = 0;
     if (lane == leader) {
       WarpChunk wc = st[bin];
@@ -226,7 +228,7 @@ __device__ __forceinline__ uint32_t chunk_append_binned(uint32_t *counter, WarpC
       st[bin] = WarpChunk{wc.base, wc.used + cnt};
     }
     first = __shfl_sync(group, first, leader);
-    idx = first + __popc(group & ((1u << lane) - 1u));
+    idx = first + __popc(group & ((1u << lane) - 1u)) * per;
   }
   __syncwarp();
   return idx;
@@ -1251,7 +1253,21 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
     return act;
   };
   // sample ls of vertex v -> at most one shadow record. All 32 lanes must call (the append is warp-collective).
-  auto draw_sample = [&](const NeeVertex &v, bool do_nee, uint32_t ls) {
+  // PAIRS (the light-only loop): the entries of a vertex's samples are reserved up front, two at a time, next to each other, so
+  // that neighbouring lanes of k_shadow trace rays that leave the same point; a sample that yields no ray leaves a skip marker.
+#ifdef RPT_NEE_PAIRS
+  constexpr bool PAIRS = !SORTED && KIND == NEE_LIGHT;
+#else
+  constexpr bool PAIRS = false;
+#endif
+  auto origin_cell = [&](float3 o) -> uint32_t {
+    const float g = (float)NEE_GRID;
+    uint32_t cx = (uint32_t)fminf(fmaxf((o.x - S.world_min.x) * S.world_inv_extent.x * g, 0.0f), g - 1.0f);
+    uint32_t cy = (uint32_t)fminf(fmaxf((o.y - S.world_min.y) * S.world_inv_extent.y * g, 0.0f), g - 1.0f);
+    uint32_t cz = (uint32_t)fminf(fmaxf((o.z - S.world_min.z) * S.world_inv_extent.z * g, 0.0f), g - 1.0f);
+    return (cz * NEE_GRID + cy) * NEE_GRID + cx;
+  };
+  auto draw_sample = [&](const NeeVertex &v, bool do_nee, uint32_t ls, uint32_t reserved) {
     bool has = false;
     float4 a = make_float4(0, 0, 0, 0), b4 = make_float4(0, 0, 0, 0);
     uint32_t c = 0;
@@ -1311,19 +1327,17 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
         }
       }
     }
-    uint32_t bin_sh = 0u;
-    if (nbins > 1) {  // origin cell
-      const float g = (float)NEE_GRID;
-      uint32_t cx = (uint32_t)fminf(fmaxf((a.x - S.world_min.x) * S.world_inv_extent.x * g, 0.0f), g - 1.0f);
-      uint32_t cy = (uint32_t)fminf(fmaxf((a.y - S.world_min.y) * S.world_inv_extent.y * g, 0.0f), g - 1.0f);
-      uint32_t cz = (uint32_t)fminf(fmaxf((a.z - S.world_min.z) * S.world_inv_extent.z * g, 0.0f), g - 1.0f);
-      bin_sh = (cz * NEE_GRID + cy) * NEE_GRID + cx;
+    uint32_t q = reserved;
+    if constexpr (!PAIRS) {
+      const uint32_t bin_sh = nbins > 1 ? origin_cell(f3(a)) : 0u;
+      q = chunk_append_binned(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow, bc);
     }
-    uint32_t q = chunk_append_binned(counts + Q_SHADOW, st_shadow, has, bin_sh, mark_shadow, bc);
     if (has) {
       sh_a[q] = a;
       sh_b[q] = b4;
       sh_c[q] = c;
+    } else if (PAIRS && do_nee) {
+      sh_c[q] = RPT_NONE;
     }
     n_shadow += has;
   };
@@ -1336,7 +1350,17 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
       const uint32_t i = tile * 32u + lane;
       NeeVertex v;
       const bool do_nee = load_vertex(i, i < n, v);
-      for (uint32_t ls = 0; ls < L; ++ls) draw_sample(v, do_nee, ls);
+      if constexpr (PAIRS) {
+        const uint32_t bin_sh = nbins > 1 ? origin_cell(v.p) : 0u;
+        for (uint32_t ls = 0; ls < L; ls += 2u) {
+          const uint32_t per = min(2u, L - ls);
+          const uint32_t base = chunk_append_binned(counts + Q_SHADOW, st_shadow, do_nee, bin_sh, mark_shadow, bc, per);
+#pragma unroll 1
+          for (uint32_t k = 0; k < per; ++k) draw_sample(v, do_nee, ls + k, base + k);
+        }
+      } else {
+        for (uint32_t ls = 0; ls < L; ++ls) draw_sample(v, do_nee, ls, RPT_NONE);
+      }
     }
   } else {
     uint2 *ring = s_ring[threadIdx.x >> 5];
@@ -1385,7 +1409,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
       __syncwarp();
       NeeVertex v;
       const bool ok = load_vertex(item.x, act, v);
-      draw_sample(v, ok, item.y);
+      draw_sample(v, ok, item.y, RPT_NONE);
     }
   }
   chunk_pad_binned(st_shadow, NEE_BINS, mark_shadow, bc);
