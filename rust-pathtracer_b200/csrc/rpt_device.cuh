@@ -123,6 +123,9 @@ struct DevScene {
   uint32_t imap_rows, imap_cols, imap_marginal_n;
   const float *imap_row_pdf, *imap_row_cdf, *imap_m_pdf, *imap_m_cdf;
   float imap_marginal_integral;
+  // Guide tables of the CDF inversions (nullptr = plain binary search): per CDF, RPT_IMAP_GUIDE entries; entry k is the first
+  // index whose CDF value reaches k / RPT_IMAP_GUIDE of the CDF's top, so an inversion searches a few entries instead of the row.
+  const uint32_t *imap_row_guide, *imap_m_guide;
   // Small-scene mode (<= RPT_SMALL_MAX leaves, no BLAS): the traversal kernels skip the BVH and test every leaf for every
   // ray in a warp-uniform loop out of shared memory (32 of 32 lanes busy, no stack); see SmallTrav below.
   uint32_t small_n;          // 0 = mode off; else the number of leaves
@@ -1328,12 +1331,32 @@ __device__ __forceinline__ float nearest_curve_eval(const float *__restrict__ si
   float t = (x - (float)index * step) / step;
   return t < 0.5f ? left : __ldg(signal + index + 1);
 }
+// Guide tables for the inversion below. guide[k] = first index i with cdf[i] >= k * (top / RPT_IMAP_GUIDE), top = the value the
+// inversion scales its sample by. Builder (k_imap_guides) and sampler evaluate the thresholds with the same f32 expression, so
+// the bracket [guide[k], guide[k + 1]] provably contains the index the full binary search returns (the CDF is non-decreasing).
+#define RPT_IMAP_GUIDE 256u
+__device__ __forceinline__ float imap_guide_threshold(uint32_t k, float top) { return (float)k * (top / (float)RPT_IMAP_GUIDE); }
+__device__ __forceinline__ float nearest_curve_eval(const float *__restrict__ signal, uint32_t n, float x);
+__device__ __forceinline__ uint32_t cdf_lower_bound(const float *__restrict__ cdf, uint32_t lo, uint32_t hi, float s) {
+  while (lo < hi) {  // first index in [lo, hi) with cdf[i] >= s, else hi
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(cdf + mid) < s) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
 __device__ __forceinline__ void nearest_cdf_sample(const float *__restrict__ pdf, const float *__restrict__ cdf, uint32_t n, float pdf_integral,
-                                                   float sample, float &x_out, float &pdf_out) {
+                                                   float sample, float &x_out, float &pdf_out, const uint32_t *__restrict__ guide = nullptr) {
   float lower_cdf = 0.0f;  // cdf.evaluate(-0.0001) is out of bounds
   float upper_cdf = nearest_curve_eval(cdf, n, 1.0f - 0.0001f);
   float s = lower_cdf + sample * (upper_cdf - lower_cdf);
   uint32_t lo = 0, hi = n;  // first index with cdf[i] >= s
+  if (guide) {
+    uint32_t k = min((uint32_t)(sample * (float)RPT_IMAP_GUIDE), RPT_IMAP_GUIDE - 1u);
+    while (k > 0u && s < imap_guide_threshold(k, upper_cdf)) --k;                           // threshold(k) <= s
+    while (k + 1u < RPT_IMAP_GUIDE && s > imap_guide_threshold(k + 1u, upper_cdf)) ++k;     // s <= threshold(k + 1), or the last bracket
+    lo = __ldg(guide + k);
+    if (k + 1u < RPT_IMAP_GUIDE) hi = __ldg(guide + k + 1u);
+  }
   while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;
     if (__ldg(cdf + mid) < s) lo = mid + 1; else hi = mid;
@@ -1401,10 +1424,11 @@ __device__ __forceinline__ void env_sample_uv(const DevScene &S, float sx, float
   }
   // ImportanceMap::sample_uv (importance_map.rs:325-357): sample.y -> row (u), sample.x -> column (v)
   float uu, row_pdf, vv, col_pdf;
-  nearest_cdf_sample(S.imap_m_pdf, S.imap_m_cdf, S.imap_marginal_n, S.imap_marginal_integral, sy, uu, row_pdf);
+  nearest_cdf_sample(S.imap_m_pdf, S.imap_m_cdf, S.imap_marginal_n, S.imap_marginal_integral, sy, uu, row_pdf, S.imap_m_guide);
   uint32_t row = (uint32_t)(uu * (float)S.imap_rows);
   if (row >= S.imap_rows) row = S.imap_rows - 1;
-  nearest_cdf_sample(S.imap_row_pdf + (size_t)row * S.imap_cols, S.imap_row_cdf + (size_t)row * S.imap_cols, S.imap_cols, 1.0f, sx, vv, col_pdf);
+  nearest_cdf_sample(S.imap_row_pdf + (size_t)row * S.imap_cols, S.imap_row_cdf + (size_t)row * S.imap_cols, S.imap_cols, 1.0f, sx, vv, col_pdf,
+                     S.imap_row_guide ? S.imap_row_guide + (size_t)row * RPT_IMAP_GUIDE : nullptr);
   float2 q = env_roundtrip(S, S.env_rot_fwd, uu, vv);
   u = q.x;
   v = q.y;

@@ -1956,6 +1956,17 @@ __global__ void __launch_bounds__(256) k_probe_bw(const float4 *__restrict__ src
   if (acc == 123.456f) *sink = acc;  // keeps the loads alive
 }
 
+// Guide tables of the importance map's CDF inversions (DevScene::imap_*_guide): one thread per (CDF, entry).
+__global__ void __launch_bounds__(256) k_imap_guides(uint32_t n_cdfs, uint32_t n, const float *__restrict__ cdfs, uint32_t *__restrict__ guides) {
+  const size_t total = (size_t)n_cdfs * RPT_IMAP_GUIDE;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(t / RPT_IMAP_GUIDE), k = (uint32_t)(t % RPT_IMAP_GUIDE);
+    const float *cdf = cdfs + (size_t)r * n;
+    const float top = nearest_curve_eval(cdf, n, 1.0f - 0.0001f);  // what nearest_cdf_sample scales its sample by
+    guides[t] = cdf_lower_bound(cdf, 0u, n, imap_guide_threshold(k, top));
+  }
+}
+
 __global__ void k_debug_env_roundtrip(uint32_t n, const float *__restrict__ u, const float *__restrict__ v, int which, float *__restrict__ uo,
                                       float *__restrict__ vo) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2723,6 +2734,30 @@ extern "C" __attribute__((visibility("hidden"))) void rpt_set_last_error(const c
 // =================================================================================================
 // C ABI
 // =================================================================================================
+// Builds the guide tables for the importance map the scene holds (called wherever its tables are installed). RPT_IMAP_GUIDES=0
+// leaves the inversions on the plain binary search; an allocation failure does too.
+static int build_imap_guides(RptScene *S) {
+  DevScene &D = S->dev;
+  D.imap_row_guide = D.imap_m_guide = nullptr;
+  const char *e = std::getenv("RPT_IMAP_GUIDES");
+  if ((e && e[0] == '0') || D.imap_rows == 0 || !D.imap_row_cdf || !D.imap_m_cdf) return 0;
+  uint32_t *g_rows = nullptr, *g_m = nullptr;
+  if (cudaMalloc(&g_rows, (size_t)D.imap_rows * RPT_IMAP_GUIDE * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&g_m, RPT_IMAP_GUIDE * sizeof(uint32_t)) != cudaSuccess) {
+    cudaGetLastError();
+    if (g_rows) cudaFree(g_rows);
+    return 0;
+  }
+  S->bufs.ptrs.push_back(g_rows);
+  S->bufs.ptrs.push_back(g_m);
+  k_imap_guides<<<S->num_sms * 4, 256, 0, S->stream>>>(D.imap_rows, D.imap_cols, D.imap_row_cdf, g_rows);
+  k_imap_guides<<<1, 256, 0, S->stream>>>(1u, D.imap_marginal_n, D.imap_m_cdf, g_m);
+  CUDA_TRY(cudaStreamSynchronize(S->stream));
+  CUDA_TRY(cudaGetLastError());
+  D.imap_row_guide = g_rows;
+  D.imap_m_guide = g_m;
+  return 0;
+}
+
 extern "C" {
 
 const char *rpt_last_error(void) { return g_error.c_str(); }
@@ -3317,6 +3352,7 @@ int rpt_scene_create(const RptSceneDesc *d, int device, RptScene **out) {
   }
   S->grid[K_FILM] = occupancy_grid(k_film, 256, film_smem, S->num_sms);
   lap("occupancy queries");
+  if (build_imap_guides(S)) return bail(1);
   *out = S;
   return 0;
 }
@@ -3552,7 +3588,7 @@ int rpt_scene_bake_importance_map(RptScene *S, const RptImapBake *B, float *row_
   D.imap_m_pdf = d_mpdf;
   D.imap_m_cdf = d_mcdf;
   if (marginal_integral) *marginal_integral = integral;
-  return 0;
+  return build_imap_guides(S);
 }
 
 int rpt_probe_bandwidth(int device, uint64_t bytes, uint32_t reps, int mode, double *gbps) {

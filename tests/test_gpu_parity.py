@@ -675,6 +675,26 @@ def test_one_level_walk_equals_two_level(monkeypatch, name):
     one.close()
 
 
+@pytest.mark.parametrize("name", ["hdri2", "hdri"])
+def test_imap_guide_tables_do_not_change_the_samples(monkeypatch, name):
+    """RPT_IMAP_GUIDES=0 inverts the importance map's CDFs with the plain binary search over the whole row; the guide tables
+    (default) bracket the same search: identical counters, film equal up to the order of the energy atomics."""
+    world, st, flat = parity.load_scene(name, 192, 108, 8)
+    monkeypatch.setenv("RPT_IMAP_GUIDES", "0")
+    plain = parity.cuda_scene(flat)
+    monkeypatch.delenv("RPT_IMAP_GUIDES")
+    guided = parity.cuda_scene(flat)
+    p = st.params(seed=47)
+    f0, c0 = plain.render_pt(p)
+    f1, c1 = guided.render_pt(p)
+    for k in ("segments", "bounce_rays", "shadow_rays", "shadow_rays_traced", "env_hits", "nee_vertices"):
+        assert getattr(c0, k) == getattr(c1, k), (name, k)
+    ok = np.isfinite(f0)
+    assert np.array_equal(ok, np.isfinite(f1)) and np.allclose(f0[ok], f1[ok], rtol=1e-5, atol=1e-9)
+    plain.close()
+    guided.close()
+
+
 @pytest.mark.parametrize("name", ["cornell", "kitchen_sink", "hdri2"])
 def test_two_stream_half_waves_equal_single_stream(monkeypatch, name):
     """RPT_OVERLAP=1 (a wave cut into two half-waves on two streams; opt-in after measurement, profiles/r02_overlap.md) renders

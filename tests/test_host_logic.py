@@ -380,6 +380,54 @@ def test_env_roundtrip_identity_against_libm():
         assert np.array_equal(ph0, ph1), (name, int((ph0 != ph1).sum()))
 
 
+def test_imap_guide_brackets_contain_the_binary_search_result():
+    """The guide tables of the importance-map CDF inversions (csrc/rpt_device.cuh: nearest_cdf_sample, RPT_IMAP_GUIDE = 256):
+    restated in numpy with the same f32 expressions. For CDFs with flat stretches, zero rows' worth of leading zeros and steep
+    steps, the first index with cdf[i] >= s always lies inside [guide[k], guide[k + 1]] for the k the sampler picks."""
+    f32 = np.float32
+    G = 256
+    rng = np.random.default_rng(11)
+
+    def top_of(cdf):  # nearest_curve_eval(cdf, n, 1 - 0.0001)
+        n = len(cdf)
+        x = f32(1.0) - f32(0.0001)
+        step = f32(1.0) / f32(n)
+        index = min(int(x / step), n - 1)
+        if index + 1 >= n:
+            return cdf[index]
+        t = (x - f32(index) * step) / step
+        return cdf[index] if t < f32(0.5) else cdf[index + 1]
+
+    for n in (7, 64, 1000, 4096):
+        for kind in range(4):
+            pdf = rng.random(n).astype(f32) ** (1 + 3 * kind)
+            if kind >= 1:
+                pdf[rng.random(n) < 0.4] = 0.0      # flat stretches
+            if kind >= 2:
+                pdf[: n // 3] = 0.0                  # leading zeros
+                pdf[rng.integers(0, n)] = f32(1e4)   # one texel holds almost everything (a sun)
+            cdf = np.cumsum(pdf, dtype=f32)
+            if kind == 3:
+                cdf = (cdf / max(cdf[-1], f32(1e-30))).astype(f32)
+            top = f32(top_of(cdf))
+            w = f32(top / f32(G))
+            thr = (np.arange(G + 1, dtype=f32) * w).astype(f32)
+            guide = np.searchsorted(cdf, thr[:G], side="left")  # first i with cdf[i] >= thr[k]
+            samples = np.concatenate([rng.random(20000).astype(f32), np.linspace(0, 1, G * 4 + 1, dtype=f32)[:-1], np.nextafter(thr[:G] / max(top, f32(1e-30)), f32(0)).astype(f32)])
+            samples = samples[(samples >= 0) & (samples < 1)]
+            s_val = (samples * top).astype(f32)
+            full = np.searchsorted(cdf, s_val, side="left")
+            k = np.minimum((samples * f32(G)).astype(np.int64), G - 1)
+            for _ in range(3):  # the two adjustment loops (they move k by at most one or two)
+                k = np.where((k > 0) & (s_val < thr[k]), k - 1, k)
+            for _ in range(3):
+                k = np.where((k + 1 < G) & (s_val > thr[np.minimum(k + 1, G)]), k + 1, k)
+            assert np.all(s_val >= thr[k]) or np.all((k == 0) | (s_val >= thr[k]))
+            lo = guide[k]
+            hi = np.where(k + 1 < G, guide[np.minimum(k + 1, G - 1)], n)
+            assert np.all((lo <= full) & (full <= hi)), (n, kind, int(np.sum(~((lo <= full) & (full <= hi)))))
+
+
 def test_exr_writer_roundtrip(pkg, tmp_path):
     """output_film's EXR payload (tonemap/mod.rs:225-247): the writer's file is read back by the package's own reader and,
     when OpenCV was built with OpenEXR, by an independent decoder."""
