@@ -84,6 +84,8 @@ enum : uint32_t {
 
 struct RenderCtx {
   uint32_t width, height, wh;
+  uint32_t tiles_x;        // 0: slot q of a frame is pixel q; else width / 8: slots run over 8 x 4 pixel tiles (slot_to_pixel)
+  uint32_t tiles_magic;    // ceil(2^32 / tiles_x) when the multiply-high division by tiles_x is exact for every tile of the frame, else 0
   uint32_t n_slots;        // slots in this wave
   uint32_t sample_base;    // global sample index of slot 0's sample
   uint32_t min_bounces, max_bounces, light_samples, only_direct;
@@ -103,6 +105,17 @@ struct WaveBuffers {
   uint32_t *counts;     // [bounces + 1][Q_COUNT] (RptScene::counts_cap rows)
   unsigned long long *work;  // [2][3]: (nodes, triangles, instances) visited by k_trace / k_shadow
 };
+
+// Which pixel the q-th slot of a frame belongs to. Row-major, a warp's 32 camera rays are a 32 x 1 strip of pixels; with
+// tiles (film width a multiple of 8, height a multiple of 4) they are an 8 x 4 block, whose rays - and the paths that follow
+// them through the queues - stay closer together in the scene. Samples are keyed by (pixel, sample index) and the film is
+// accumulated per pixel, so the mapping changes the order of the work, not the image.
+__device__ __forceinline__ uint32_t slot_to_pixel(const RenderCtx &R, uint32_t q) {
+  if (R.tiles_x == 0u) return q;
+  const uint32_t tile = q >> 5, l = q & 31u;
+  const uint32_t ty = R.tiles_magic ? __umulhi(tile, R.tiles_magic) : tile / R.tiles_x, tx = tile - ty * R.tiles_x;
+  return ((ty << 2) + (l >> 3)) * R.width + (tx << 3) + (l & 7u);
+}
 
 __device__ __forceinline__ float3 rec_origin(const PathRec &r) {
   float3 p = f3(r.r0), n = f3(r.r1);
@@ -346,7 +359,7 @@ __device__ __forceinline__ void flush_work(const TraceWork &w, unsigned long lon
 // ---------------------------------------------------------------------------------------------
 // The camera vertex of sample `slot` (pt.rs:397-446): film jitter, wavelength, camera ray.
 __device__ __forceinline__ PathRec camera_record(const RenderCtx &R, uint32_t slot) {
-    uint32_t pixel = slot % R.wh, sample = R.sample_base + slot / R.wh;
+    uint32_t pixel = slot_to_pixel(R, slot % R.wh), sample = R.sample_base + slot / R.wh;
     uint32_t px = pixel % R.width, py = pixel / R.width;
     RptRand4 s0 = rpt_philox(R.seed, pixel, sample, 0);
     RptRand4 s1 = rpt_philox(R.seed, pixel, sample, 1);
@@ -815,7 +828,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade_surfa
       frame = frame_from_normal(sh.n);
       float3 wi = normalized(to_local(frame, -d));  // integrator/utils.rs:175-176
       const RptMaterial m = S.materials[RPT_MAT_INDEX(sh.material)];
-      pixel = slot % R.wh;
+      pixel = slot_to_pixel(R, slot % R.wh);
       sample = R.sample_base + slot / R.wh;
       RptRand4 s = rpt_philox(R.seed, pixel, sample, rpt_block_bsdf(bounce, L));
 
@@ -1077,7 +1090,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, VERTEX_MIN_BLOCKS) k_shade_vert
       hn = sh.n;
       Frame frame = frame_from_normal(sh.n);
       float3 wi = normalized(to_local(frame, -d));  // integrator/utils.rs:175-176
-      const uint32_t pixel = slot % R.wh, sample = R.sample_base + slot / R.wh;
+      const uint32_t pixel = slot_to_pixel(R, slot % R.wh), sample = R.sample_base + slot / R.wh;
       RptRand4 s = rpt_philox(R.seed, pixel, sample, rpt_block_bsdf(bounce, L));
 
       // ---- generate_and_evaluate
@@ -1236,7 +1249,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
     v.beta = r0.w;
     v.lambda = r1.w;
     v.slot = __float_as_uint(r2.w);
-    v.pixel = v.slot % R.wh;
+    v.pixel = slot_to_pixel(R, v.slot % R.wh);
     v.sample = R.sample_base + v.slot / R.wh;
     v.frame = frame_from_normal(v.nrm);
     v.gp.alpha = 1.0f;
@@ -1382,7 +1395,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_nee(DevScene S, RenderCtx 
           uint32_t slot = RPT_NONE;
           if (i < n) slot = __float_as_uint(__ldg(reinterpret_cast<const float4 *>(nee + i) + 2).w);
           do_nee = slot != RPT_NONE;
-          pixel = slot % R.wh;
+          pixel = slot_to_pixel(R, slot % R.wh);
           sample = R.sample_base + slot / R.wh;
           ls = 0u;
         }
@@ -1679,10 +1692,11 @@ __global__ void __launch_bounds__(256) k_film(DevScene S, RenderCtx R, const flo
   __syncthreads();
   uint32_t spp = R.n_slots / R.wh;
   uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < R.wh; pixel += stride) {
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < R.wh; q += stride) {
+    const uint32_t pixel = slot_to_pixel(R, q);
     float X = 0.0f, Y = 0.0f, Z = 0.0f;
     for (uint32_t s = 0; s < spp; ++s) {
-      float e = acc[(size_t)s * R.wh + pixel];
+      float e = acc[(size_t)s * R.wh + q];
       if (e == 0.0f) continue;
       RptRand4 s0 = rpt_philox(R.seed, pixel, R.sample_base + s, 0);
       float lambda = R.lambda_lo + s0.z * (R.lambda_hi - R.lambda_lo);
@@ -2384,6 +2398,13 @@ RenderCtx make_ctx(const RptScene *S, const RptRenderParams *P) {
   R.lambda_hi = P->lambda_hi;
   R.seed = P->seed;
   R.cam = S->cameras[P->camera];
+  {
+    const char *e = std::getenv("RPT_TILED");  // RPT_TILED=0: row-major slots
+    R.tiles_x = (P->width % 8u == 0u && P->height % 4u == 0u && !(e && e[0] == '0')) ? P->width / 8u : 0u;
+    // floor(n * ceil(2^32 / d) / 2^32) == n / d for every n with n * d < 2^32; n < tiles_x * (height / 4)
+    const uint64_t d = R.tiles_x, n_max = d * (P->height / 4u);
+    R.tiles_magic = (d > 1 && n_max * d < (1ull << 32)) ? (uint32_t)(((1ull << 32) + d - 1) / d) : 0u;
+  }
   return R;
 }
 
@@ -3398,6 +3419,7 @@ int rpt_trace_primary(RptScene *S, const RptRenderParams *P, uint32_t *inst, uin
   size_t wh = (size_t)P->width * P->height;
   if (int rc = ensure_wave(S, wh, wh * P->light_samples, 1)) return rc;
   RenderCtx R = make_ctx(S, P);
+  R.tiles_x = 0;  // (hit records are returned in slot order = pixel order)
   R.n_slots = (uint32_t)wh;
   R.sample_base = P->spp_offset;
   WaveBuffers &w = S->wave;

@@ -695,6 +695,28 @@ def test_imap_guide_tables_do_not_change_the_samples(monkeypatch, name):
     guided.close()
 
 
+@pytest.mark.parametrize("name,w,h", [("cornell", 192, 108), ("instanced_monkeys", 192, 108), ("hdri2", 160, 88), ("kitchen_sink", 64, 4), ("gem", 8, 64)])
+def test_tiled_slots_render_the_same_film(monkeypatch, name, w, h):
+    """Slots of a frame run over 8 x 4 pixel tiles when the film's width is a multiple of 8 and its height of 4 (RPT_TILED=0:
+    row-major). Samples are keyed by (pixel, sample) and accumulated per pixel: identical counters, film equal up to the order
+    of the energy atomics, for one wave and for several."""
+    world, st, flat = parity.load_scene(name, w, h, 6)
+    monkeypatch.setenv("RPT_TILED", "0")
+    rows = parity.cuda_scene(flat)
+    f0, c0 = rows.render_pt(st.params(seed=53))
+    monkeypatch.delenv("RPT_TILED")
+    f1, c1 = rows.render_pt(st.params(seed=53))
+    monkeypatch.setenv("RPT_WAVE_SLOTS_MAX", str(2 * w * h))  # three waves of 2 spp
+    f2, c2 = rows.render_pt(st.params(seed=53))
+    for c in (c1, c2):
+        for k in ("camera_rays", "segments", "bounce_rays", "shadow_rays", "shadow_rays_traced", "env_hits", "nee_vertices"):
+            assert getattr(c0, k) == getattr(c, k), (name, k)
+    ok = np.isfinite(f0)
+    for f in (f1, f2):
+        assert np.array_equal(ok, np.isfinite(f)) and np.allclose(f0[ok], f[ok], rtol=1e-5, atol=1e-9), name
+    rows.close()
+
+
 @pytest.mark.parametrize("name", ["cornell", "kitchen_sink", "hdri2"])
 def test_two_stream_half_waves_equal_single_stream(monkeypatch, name):
     """RPT_OVERLAP=1 (a wave cut into two half-waves on two streams; opt-in after measurement, profiles/r02_overlap.md) renders
